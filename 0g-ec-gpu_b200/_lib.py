@@ -1,0 +1,171 @@
+"""ctypes binding of include/msm_b200.h.
+
+There is no fallback of any kind here: if libmsm_b200.so is missing or does not export a symbol
+the header declares, importing callers get an exception.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_LIB = os.path.join(_HERE, "libmsm_b200.so")
+_HEADER = os.path.join(_ROOT, "include", "msm_b200.h")
+
+BN254_G1 = 0
+BLS12_381_G1 = 1
+
+MSM_OK, MSM_ERR_INVALID, MSM_ERR_CUDA, MSM_ERR_BUSY, MSM_ERR_ABORTED, MSM_ERR_NO_DEVICE, MSM_ERR_TOO_LARGE = range(7)
+
+
+def fq_bytes(curve: int) -> int:
+    return 32 if curve == BN254_G1 else 48
+
+
+class EcError(Exception):
+    """ec_gpu_program::EcError (ec-gpu-program/src/lib.rs:11-32)."""
+
+
+class EcErrorSimple(EcError):
+    pass
+
+
+class EcErrorAborted(EcError):
+    pass
+
+
+class EcErrorGpuTools(EcError):
+    pass
+
+
+class CudaError(Exception):
+    """rustacuda::error::CudaError as surfaced by ag_cuda_ec (CudaResult)."""
+
+    def __init__(self, name, detail=""):
+        super().__init__(f"{name}: {detail}" if detail else name)
+        self.name = name
+
+
+class Timings(ctypes.Structure):
+    _fields_ = [
+        ("h2d_ms", ctypes.c_float),
+        ("sort_ms", ctypes.c_float),
+        ("accumulate_ms", ctypes.c_float),
+        ("reduce_ms", ctypes.c_float),
+        ("total_ms", ctypes.c_float),
+        ("window_bits", ctypes.c_uint32),
+        ("num_windows", ctypes.c_uint32),
+        ("num_entries", ctypes.c_uint64),
+        ("kernel_launches", ctypes.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def library_path() -> str:
+    return _LIB
+
+
+def build_library(force: bool = False) -> str:
+    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-s"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args)
+    return _LIB
+
+
+def header_symbols() -> list[str]:
+    """Every function the C header declares."""
+    text = open(_HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msm_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise ImportError(
+            f"{_LIB} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+            "(or __graft_entry__.build()). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(_LIB)
+    vp, sz, i32, u32, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    sig = {
+        "msm_device_count": ([], i32),
+        "msm_ctx_create": ([i32, ctypes.POINTER(i32), i32, pp], i32),
+        "msm_ctx_destroy": ([vp], i32),
+        "msm_ctx_num_devices": ([vp], i32),
+        "msm_set_abort_flag": ([vp, vp], i32),
+        "msm_last_error": ([vp], ctypes.c_char_p),
+        "msm_last_timings": ([vp, ctypes.POINTER(Timings)], i32),
+        "msm_set_window_bits": ([vp, u32], i32),
+        "msm_bases_upload": ([vp, vp, sz, pp], i32),
+        "msm_bases_upload_sharded": ([vp, vp, sz, pp], i32),
+        "msm_bases_wrap_device": ([vp, vp, sz, pp], i32),
+        "msm_bases_size_bytes": ([vp], sz),
+        "msm_bases_num_points": ([vp], sz),
+        "msm_bases_free": ([vp], i32),
+        "msm_multiple_multiexp": ([vp, vp, vp, sz, u32, u32, i32, vp], i32),
+        "msm_multiple_multiexp_device": ([vp, vp, vp, sz, u32, vp], i32),
+        "msm_multiexp": ([vp, vp, vp, sz, vp], i32),
+        "msm_multiexp_resident": ([vp, vp, sz, vp, sz, vp], i32),
+        "msm_sum_points_device": ([vp, vp, sz, vp], i32),
+        "msm_to_affine": ([vp, vp, sz, i32, vp, vp], i32),
+        "msm_synth_points_device": ([vp, u64, sz, sz, vp], i32),
+        "msm_synth_scalars_device": ([vp, u64, sz, sz, vp], i32),
+        "msm_test_fq_op": ([vp, i32, vp, vp, vp, sz], i32),
+        "msm_test_ec_op": ([vp, i32, vp, vp, vp, sz], i32),
+        "msm_device_alloc": ([vp, sz, pp], i32),
+        "msm_device_free": ([vp, vp], i32),
+        "msm_memcpy_h2d": ([vp, vp, vp, sz], i32),
+        "msm_memcpy_d2h": ([vp, vp, vp, sz], i32),
+        "msm_host_register": ([vp, sz], i32),
+        "msm_host_unregister": ([vp], i32),
+        "msm_version": ([], ctypes.c_char_p),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(rc: int, ctx=None, cuda_style: bool = False):
+    """Map an msm_status to the reference's error types."""
+    if rc == MSM_OK:
+        return
+    lib = load_library()
+    msg = lib.msm_last_error(ctx)
+    msg = msg.decode() if msg else ""
+    if cuda_style:
+        # ag_cuda_ec returns CudaResult<_>
+        if rc == MSM_ERR_BUSY:
+            raise CudaError("ContextAlreadyInUse", msg)
+        if rc == MSM_ERR_NO_DEVICE:
+            raise CudaError("NoDevice", msg or "No working GPUs found!")
+        if rc == MSM_ERR_INVALID:
+            raise CudaError("InvalidValue", msg)
+        if rc == MSM_ERR_TOO_LARGE:
+            raise CudaError("InvalidValue", "size exceeds the u32 index space")
+        raise CudaError("UnknownError", msg)
+    if rc == MSM_ERR_ABORTED:
+        raise EcErrorAborted("GPU call was aborted!")
+    if rc == MSM_ERR_NO_DEVICE:
+        raise EcErrorSimple("No working GPUs found!")
+    if rc == MSM_ERR_CUDA:
+        raise EcErrorGpuTools(msg)
+    if rc == MSM_ERR_BUSY:
+        raise EcErrorGpuTools("context already in use")
+    raise EcErrorSimple(msg or f"msm_status {rc}")

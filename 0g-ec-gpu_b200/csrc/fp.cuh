@@ -1,0 +1,242 @@
+// fp.cuh -- prime-field arithmetic on N 32-bit limbs in Montgomery form (R = 2^(32 N)).
+//
+// Replaces the generated field layer of the reference: FIELD_add/sub/double/mul/sqr
+// (ag-build/cl/field.cl:14-69, 85-263, 313-325) and the per-field constants emitted by
+// ag-build/src/source/template.rs:35-71.  Constants are fixed templates for BN254 Fq and
+// BLS12-381 Fq (values cross-checked against oracle/pyref.py in tests/test_constants.py).
+//
+// All values are kept fully reduced in [0, p).  Layout: little-endian uint32 limbs, identical to
+// the reference's FIELD struct (ag-build/src/source/template.rs:52).
+#pragma once
+#include "ptx.cuh"
+
+namespace msm {
+
+// ---------------------------------------------------------------------------------------------
+// Field parameter packs.  P(i) / ONE(i) / R2(i) fold to immediates after unrolling.
+// ---------------------------------------------------------------------------------------------
+struct Bn254Fq {
+  static constexpr int N = 8;
+  static constexpr uint32_t INV = 0xe4866389u;  // -p^-1 mod 2^32 (limb.rs:65-72)
+  static MSM_HD constexpr uint32_t P(int i) {
+    constexpr uint32_t t[N] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return t[i];
+  }
+  static MSM_HD constexpr uint32_t ONE(int i) {  // R mod p
+    constexpr uint32_t t[N] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                               0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return t[i];
+  }
+  static MSM_HD constexpr uint32_t R2(int i) {  // R^2 mod p
+    constexpr uint32_t t[N] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                               0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return t[i];
+  }
+  static constexpr uint32_t CURVE_B = 3;  // y^2 = x^3 + 3
+};
+
+struct Bls381Fq {
+  static constexpr int N = 12;
+  static constexpr uint32_t INV = 0xfffcfffdu;
+  static MSM_HD constexpr uint32_t P(int i) {
+    constexpr uint32_t t[N] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu,
+                               0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u,
+                               0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+    return t[i];
+  }
+  static MSM_HD constexpr uint32_t ONE(int i) {
+    constexpr uint32_t t[N] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu,
+                               0x53c758bau, 0x5f489857u, 0x70525745u, 0x77ce5853u,
+                               0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+    return t[i];
+  }
+  static MSM_HD constexpr uint32_t R2(int i) {
+    constexpr uint32_t t[N] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u,
+                               0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u,
+                               0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+    return t[i];
+  }
+  static constexpr uint32_t CURVE_B = 4;  // y^2 = x^3 + 4
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class P> struct Fp {
+  static constexpr int N = P::N;
+  uint32_t v[N];
+};
+
+template <class P> MSM_HD Fp<P> fp_zero() {
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r.v[i] = 0;
+  return r;
+}
+template <class P> MSM_HD Fp<P> fp_one() {
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r.v[i] = P::ONE(i);
+  return r;
+}
+template <class P> MSM_HD bool fp_is_zero(const Fp<P>& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) o |= a.v[i];
+  return o == 0;
+}
+template <class P> MSM_HD bool fp_eq(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) o |= a.v[i] ^ b.v[i];
+  return o == 0;
+}
+
+// r = (r >= p) ? r - p : r      (r < 2p on entry)
+template <class P> MSM_HD void fp_csub_p(uint32_t* r) {
+  constexpr int N = P::N;
+  uint32_t t[N];
+  t[0] = sub_cc(r[0], P::P(0));
+#pragma unroll
+  for (int i = 1; i < N; i++) t[i] = subc_cc(r[i], P::P(i));
+  uint32_t borrow = subc(0u, 0u);  // 0xffffffff when r < p
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+template <class P> MSM_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+  r.v[N - 1] = addc(a.v[N - 1], b.v[N - 1]);  // p < 2^(32N-2): no carry out
+  fp_csub_p<P>(r.v);
+  return r;
+}
+
+template <class P> MSM_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t mask = subc(0u, 0u);  // 0xffffffff when a < b
+  r.v[0] = add_cc(r.v[0], P::P(0) & mask);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(r.v[i], P::P(i) & mask);
+  r.v[N - 1] = addc(r.v[N - 1], P::P(N - 1) & mask);
+  return r;
+}
+
+template <class P> MSM_HD Fp<P> fp_dbl(const Fp<P>& a) { return fp_add<P>(a, a); }
+
+template <class P> MSM_HD Fp<P> fp_neg(const Fp<P>& a) {
+  constexpr int N = P::N;
+  // p - a, mapped to 0 when a == 0
+  uint32_t nz = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) nz |= a.v[i];
+  uint32_t mask = nz ? 0xffffffffu : 0u;
+  Fp<P> r;
+  r.v[0] = sub_cc(P::P(0) & mask, a.v[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.v[i] = subc_cc(P::P(i) & mask, a.v[i]);
+  r.v[N - 1] = subc(P::P(N - 1) & mask, a.v[N - 1]);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery product, coarsely-integrated operand scanning with two accumulators that hold the
+// even-aligned (E) and odd-aligned (O) 64-bit columns, so that every 32x32->64 product is one
+// wide multiply-add on a 64-bit-aligned register pair and the carry chain of a row never has to
+// ripple across the whole accumulator.  Per row i:   T += a*b[i];  m = T*INV mod 2^32;
+// T += m*p;  T >>= 32.  The shift swaps the roles of E and O (the old E, shifted by 64 bits,
+// becomes the new O; its orphan limb E[1] is folded into the new E[0] with the carry entering
+// the next row's O chain).  2N^2 + N multiplier-pipe operations (N=8: 136).
+//
+// Invariant: T = sum E[k] 2^(32k) + 2^32 sum O[k] 2^(32k) < 2^(32(N+1)) at every point (because
+// p < 2^(32N-2)), hence neither chain ever carries out of O[N-1] and E's carry-out is added to
+// O[N-1] (same weight 2^(32N)).
+// ---------------------------------------------------------------------------------------------
+template <class P, bool FIRST>
+MSM_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
+  constexpr int N = P::N;
+  if (FIRST) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      mul_wide(E[j], E[j + 1], a[j], bi);
+      mul_wide(O[j], O[j + 1], a[j + 1], bi);
+    }
+  } else {
+    // E is last row's O; O is last row's E (its limb 0 is zero, limb 1 is the orphan).
+    E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) madc_wide_cc3(O[j], O[j + 1], a[j + 1], bi, O[j + 2], O[j + 3]);
+    madc_wide_0(O[N - 2], O[N - 1], a[N - 1], bi);
+    mad_wide_cc(E[0], E[1], a[0], bi);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], a[j], bi);
+    O[N - 1] = addc(O[N - 1], 0u);
+  }
+  const uint32_t m = mul_lo(E[0], P::INV);
+  mad_wide_cc(O[0], O[1], P::P(1), m);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(O[j], O[j + 1], P::P(j + 1), m);
+  mad_wide_cc(E[0], E[1], P::P(0), m);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], P::P(j), m);
+  O[N - 1] = addc(O[N - 1], 0u);
+}
+
+template <class P> MSM_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  static_assert(N % 2 == 0, "even limb count required");
+  uint32_t X[N], Y[N];
+  mont_row<P, true>(X, Y, a.v, b.v[0]);
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    mont_row<P, false>(Y, X, a.v, b.v[i]);
+    if (i + 1 < N) mont_row<P, false>(X, Y, a.v, b.v[i + 1]);
+  }
+  // last row had E = Y, O = X:  result = (E >> 32) + O
+  Fp<P> r;
+  r.v[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
+  r.v[N - 1] = addc(X[N - 1], 0u);
+  fp_csub_p<P>(r.v);
+  return r;
+}
+
+template <class P> MSM_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
+
+// Montgomery <-> canonical
+template <class P> MSM_HD Fp<P> fp_to_mont(const Fp<P>& a) {
+  Fp<P> r2;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r2.v[i] = P::R2(i);
+  return fp_mul<P>(a, r2);
+}
+template <class P> MSM_HD Fp<P> fp_from_mont(const Fp<P>& a) {
+  Fp<P> o = fp_zero<P>();
+  o.v[0] = 1;
+  return fp_mul<P>(a, o);
+}
+
+// a^(p-2); a != 0.  Only used once per result / per synthetic-input batch, never in the hot loop.
+template <class P> MSM_COLD Fp<P> fp_inv(const Fp<P>& a) {
+  constexpr int N = P::N;
+  uint32_t e[N];
+  e[0] = sub_cc(P::P(0), 2u);
+#pragma unroll
+  for (int i = 1; i < N; i++) e[i] = subc_cc(P::P(i), 0u);
+  Fp<P> acc = fp_one<P>();
+  Fp<P> base = a;
+  for (int i = 0; i < 32 * N; i++) {
+    if ((e[i >> 5] >> (i & 31)) & 1) acc = fp_mul<P>(acc, base);
+    base = fp_sqr<P>(base);
+  }
+  return acc;
+}
+
+}  // namespace msm

@@ -1,0 +1,513 @@
+// kernels.cuh -- the device side of the MSM engine.
+//
+// Pipeline for one call (T = num_chunks scalar-side tasks, W windows of c bits, B = 2^(c-1)
+// buckets per (task, window), `lines` base lines sharing the scalar row):
+//
+//   k_digits<COUNT>   signed-digit (Booth) decomposition of every scalar, histogram of bucket ids
+//   k_scan_*          exclusive scan of the histogram  -> bucket_start[NB+1]
+//   k_digits<SCATTER> same decomposition, scatter (point index | sign) into bucket order
+//   k_accumulate      one thread per fixed-size slice of the sorted entry list; XYZZ mixed adds;
+//                     whole buckets are written directly, buckets cut by a slice boundary go to
+//                     per-slice partial slots
+//   k_fixup           combines the partial slots of cut buckets, writes infinity to empty buckets
+//   k_bucket_reduce   running-sum reduction  sum_b b*S_b  split over threads + shared-memory tree
+//   k_window_combine  sums the per-window partials, Horner over windows, XYZZ -> Jacobian
+//
+// This replaces POINT_multiexp / POINT_multiexp_chunk / POINT_aggregate_chunk
+// (ag-build/cl/multiexp.cl:62-264), where one thread owns a whole (task, window) and scans the
+// chunk serially against buckets in global memory.
+#pragma once
+#include "ec.cuh"
+
+namespace msm {
+
+struct Geometry {
+  uint32_t L;          // scalars per row actually used (= num_chunks * chunk_len)
+  uint32_t chunk_len;  // points per task
+  uint32_t num_chunks; // scalar-side tasks
+  uint32_t c;          // window bits
+  uint32_t W;          // windows
+  uint32_t B;          // buckets per (task, window) = 2^(c-1)
+  uint32_t NB;         // num_chunks * W * B
+  uint32_t scalar_bits;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Signed-digit decomposition.  k = sum_w d_w 2^(c w),  d_w in [-(2^(c-1) - 1), 2^(c-1)].
+// W*c >= scalar_bits + 1 guarantees no carry out of the top window (the reference's kernel drops
+// that carry, TODO at ag-build/cl/multiexp.cl:60).  Bits are taken LSB-first from the canonical
+// little-endian scalar (the reference indexes MSB-first, ag-build/cl/field.cl:380-392; the digit
+// set is a free choice because the result does not depend on it).
+// f(w, bucket_1based, negative) is called for every non-zero digit.
+// ---------------------------------------------------------------------------------------------
+template <class F> MSM_D void for_each_digit(const uint32_t k[8], uint32_t c, uint32_t W, F&& f) {
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t mask = (1u << c) - 1u;
+  uint64_t buf = 0;
+  uint32_t nbits = 0, w = 0, carry = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    buf |= (uint64_t)k[j] << nbits;
+    nbits += 32;
+    while (nbits >= c && w < W) {
+      uint32_t raw = ((uint32_t)buf & mask) + carry;
+      buf >>= c;
+      nbits -= c;
+      carry = raw > half;
+      if (raw != 0 && raw != (1u << c)) {
+        if (carry) f(w, (1u << c) - raw, true);
+        else f(w, raw, false);
+      }
+      w++;
+    }
+  }
+  // remaining high bits (fewer than c)
+  while (w < W) {
+    uint32_t raw = ((uint32_t)buf & mask) + carry;
+    buf >>= c;
+    carry = raw > half;
+    if (raw != 0 && raw != (1u << c)) {
+      if (carry) f(w, (1u << c) - raw, true);
+      else f(w, raw, false);
+    }
+    w++;
+  }
+}
+
+MSM_D void load_scalar(const uint32_t* scalars, uint32_t i, uint32_t k[8]) {
+  const uint4* p = reinterpret_cast<const uint4*>(scalars) + 2 * (size_t)i;
+  uint4 a = __ldg(p), b = __ldg(p + 1);
+  k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
+  k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+}
+
+// SCATTER = false: counts[g]++ ;  SCATTER = true: entries[cursor[g]++] = i | sign<<31
+template <bool SCATTER>
+__global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
+                         uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= geo.L) return;
+  uint32_t k[8];
+  load_scalar(scalars, i, k);
+  const uint32_t task = i / geo.chunk_len;
+  const uint32_t base = task * geo.W;
+  for_each_digit(k, geo.c, geo.W, [&](uint32_t w, uint32_t bucket, bool neg) {
+    const uint32_t g = (base + w) * geo.B + (bucket - 1);
+    if (SCATTER) {
+      const uint32_t pos = atomicAdd(&counts_or_cursor[g], 1u);
+      entries[pos] = i | (neg ? 0x80000000u : 0u);
+    } else {
+      atomicAdd(&counts_or_cursor[g], 1u);
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive scan of n uint32 (three small kernels; n <= a few million, HBM-trivial).
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 8;  // per thread
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[SCAN_BLOCK / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = lane < SCAN_BLOCK / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < SCAN_BLOCK / 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    if (lane < SCAN_BLOCK / 32) warp_sums[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t warp_off = wid ? warp_sums[wid - 1] : 0;
+  *total = warp_sums[SCAN_BLOCK / 32 - 1];
+  __syncthreads();
+  return warp_off + x - v;
+}
+
+__global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+                             uint32_t* __restrict__ tile_sums) {
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) {
+    v[j] = base + j < n ? in[base + j] : 0;
+    s += v[j];
+  }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(s, &total);
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) {
+    if (base + j < n) out[base + j] = off;
+    off += v[j];
+  }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// single block: exclusive scan of tile sums in place, total written to *grand_total
+__global__ void k_scan_tile_sums(uint32_t* tile_sums, uint32_t n_tiles, uint32_t* grand_total) {
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n_tiles; base += SCAN_BLOCK) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < n_tiles ? tile_sums[i] : 0;
+    uint32_t total;
+    uint32_t off = block_exclusive_scan(v, &total);
+    if (i < n_tiles) tile_sums[i] = carry + off;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *grand_total = carry;
+}
+// out[i] += tile_offset; also writes the closing element out[n] = grand_total and a copy (cursor)
+__global__ void k_scan_finish(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_sums,
+                              const uint32_t* __restrict__ grand_total, uint32_t* __restrict__ cursor) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t v = out[i] + tile_sums[i / SCAN_TILE];
+    out[i] = v;
+    cursor[i] = v;
+  } else if (i == n) {
+    out[n] = *grand_total;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Point loads: 128-bit loads, read-only path.
+// ---------------------------------------------------------------------------------------------
+template <class P> MSM_D Affine<P> load_affine(const Affine<P>* p) {
+  Affine<P> r;
+  constexpr int V = (2 * P::N) / 4;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int j = 0; j < V; j++) {
+    uint4 t = __ldg(q + j);
+    o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
+  }
+  return r;
+}
+template <class T> MSM_D void store_vec(T* dst, const T& v) {
+  constexpr int V = sizeof(T) / 16;
+  uint4* q = reinterpret_cast<uint4*>(dst);
+  const uint32_t* o = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int j = 0; j < V; j++) q[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+template <class T> MSM_D T load_vec(const T* src) {
+  T r;
+  constexpr int V = sizeof(T) / 16;
+  const uint4* q = reinterpret_cast<const uint4*>(src);
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int j = 0; j < V; j++) {
+    uint4 t = q[j];
+    o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
+  }
+  return r;
+}
+
+// largest g in [0, NB) with bucket_start[g] <= pos  (pos < bucket_start[NB])
+MSM_D uint32_t find_bucket(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t pos) {
+  uint32_t lo = 0, hi = NB;  // invariant: bucket_start[lo] <= pos < bucket_start[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(bucket_start + mid) <= pos) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bucket accumulation.  Thread t of line `blockIdx.y` owns sorted entries [t*S, (t+1)*S).
+// ---------------------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(128)
+k_accumulate(const Affine<P>* __restrict__ bases, uint32_t line_stride,
+             const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start,
+             uint32_t NB, const uint32_t* __restrict__ E_ptr, uint32_t S, uint32_t n_slices,
+             Xyzz<P>* __restrict__ bucket_acc, Xyzz<P>* __restrict__ partials) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t E = __ldg(E_ptr);  // = bucket_start[NB], number of non-zero digits
+  if (t >= n_slices || (uint64_t)t * S >= E) return;
+  const uint32_t line = blockIdx.y;
+  bases += (size_t)line * line_stride;
+  bucket_acc += (size_t)line * NB;
+  partials += (size_t)line * 2 * n_slices;
+
+  const uint32_t s = t * S;
+  const uint32_t e = min(s + S, E);
+  uint32_t g = find_bucket(bucket_start, NB, s);
+  uint32_t gend = __ldg(bucket_start + g + 1);
+  bool started_before = __ldg(bucket_start + g) < s;
+  Xyzz<P> acc = xyzz_inf<P>();
+
+  for (uint32_t pos = s; pos < e; pos++) {
+    if (pos == gend) {
+      // bucket g is complete: flush and move to the next non-empty bucket
+      store_vec(started_before ? &partials[2 * t] : &bucket_acc[g], acc);
+      acc = xyzz_inf<P>();
+      started_before = false;
+      do {
+        g++;
+        gend = __ldg(bucket_start + g + 1);
+      } while (gend == pos);
+    }
+    const uint32_t ent = __ldg(entries + pos);
+    Affine<P> pt = load_affine<P>(bases + (ent & 0x7fffffffu));
+    if (!aff_is_identity<P>(pt)) {
+      pt = aff_cneg<P>(pt, (ent >> 31) != 0);
+      xyzz_madd<P>(acc, pt);
+    }
+  }
+  if (gend == e) {
+    store_vec(started_before ? &partials[2 * t] : &bucket_acc[g], acc);
+  } else {
+    store_vec(started_before ? &partials[2 * t] : &partials[2 * t + 1], acc);
+  }
+}
+
+// One thread per bucket: empty -> infinity; cut by slice boundaries -> sum of its partial slots.
+template <class P>
+__global__ void __launch_bounds__(128)
+k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
+        Xyzz<P>* __restrict__ bucket_acc, const Xyzz<P>* __restrict__ partials) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= NB) return;
+  const uint32_t line = blockIdx.y;
+  bucket_acc += (size_t)line * NB;
+  partials += (size_t)line * 2 * n_slices;
+  const uint32_t start = bucket_start[g], end = bucket_start[g + 1];
+  if (start == end) {
+    store_vec(&bucket_acc[g], xyzz_inf<P>());
+    return;
+  }
+  const uint32_t t0 = start / S, t1 = (end - 1) / S;
+  if (t0 == t1) return;  // written directly by k_accumulate
+  Xyzz<P> acc = load_vec(&partials[2 * t0 + 1]);
+  for (uint32_t t = t0 + 1; t <= t1; t++) acc = xyzz_add<P>(acc, load_vec(&partials[2 * t]));
+  store_vec(&bucket_acc[g], acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bucket reduction: for every group (line, task, window) compute sum_{b=1..B} b * S_b.
+// Thread j owns Q consecutive buckets: local running sum, plus (first_weight-1) * (plain sum);
+// then a segmented shared-memory tree over RW threads.  Output: one partial per RW threads.
+// ---------------------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(128)
+k_bucket_reduce(const Xyzz<P>* __restrict__ bucket_acc, uint32_t n_threads, uint32_t B, uint32_t Q,
+                uint32_t RW, Xyzz<P>* __restrict__ out) {
+  extern __shared__ uint4 smem_raw[];
+  Xyzz<P>* sh = reinterpret_cast<Xyzz<P>*>(smem_raw);
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  Xyzz<P> res = xyzz_inf<P>();
+  if (tid < n_threads) {
+    const size_t f = (size_t)tid * Q;
+    const uint32_t b0 = (uint32_t)(f % B);  // weight of bucket f+k is b0 + k + 1
+    Xyzz<P> run = xyzz_inf<P>();
+    for (int k = (int)Q - 1; k >= 0; k--) {
+      run = xyzz_add<P>(run, load_vec(&bucket_acc[f + k]));
+      res = xyzz_add<P>(res, run);
+    }
+    if (b0) res = xyzz_add<P>(res, xyzz_mul_small<P>(run, b0));
+  }
+  sh[threadIdx.x] = res;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & (RW - 1);
+  for (uint32_t stride = RW >> 1; stride >= 1; stride >>= 1) {
+    if (lane < stride) {
+      res = xyzz_add<P>(res, sh[threadIdx.x + stride]);
+      sh[threadIdx.x] = res;
+    }
+    __syncthreads();
+  }
+  if (lane == 0 && tid < n_threads) store_vec(&out[tid / RW], res);
+}
+
+// One block per task (line, chunk): thread w sums the PG partials of window w; thread 0 folds the
+// windows Horner-style (c doublings per step) and writes the Jacobian result.
+template <class P>
+__global__ void k_window_combine(const Xyzz<P>* __restrict__ group_partials, uint32_t W, uint32_t PG,
+                                 uint32_t c, Jacobian<P>* __restrict__ out) {
+  extern __shared__ uint4 smem_raw[];
+  Xyzz<P>* sh = reinterpret_cast<Xyzz<P>*>(smem_raw);
+  const uint32_t task = blockIdx.x;
+  for (uint32_t w = threadIdx.x; w < W; w += blockDim.x) {
+    const Xyzz<P>* src = group_partials + ((size_t)task * W + w) * PG;
+    Xyzz<P> s = load_vec(src);
+    for (uint32_t k = 1; k < PG; k++) s = xyzz_add<P>(s, load_vec(src + k));
+    sh[w] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Xyzz<P> acc = sh[W - 1];
+    for (int w = (int)W - 2; w >= 0; w--) {
+      for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl<P>(acc);
+      acc = xyzz_add<P>(acc, sh[w]);
+    }
+    out[task] = xyzz_to_jacobian<P>(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small helpers: sum of Jacobian points, Jacobian -> affine, per-primitive test kernels
+// (counterpart of ag-build/cl/test.cl), synthetic inputs.
+// ---------------------------------------------------------------------------------------------
+template <class P>
+__global__ void k_sum_points(const Jacobian<P>* __restrict__ in, uint32_t count, Jacobian<P>* __restrict__ out) {
+  if (blockIdx.x || threadIdx.x) return;
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (uint32_t i = 0; i < count; i++) acc = xyzz_add<P>(acc, xyzz_from_jacobian<P>(in[i]));
+  out[0] = xyzz_to_jacobian<P>(acc);
+}
+
+template <class P>
+__global__ void k_to_affine(const Jacobian<P>* __restrict__ in, uint32_t count, int mont_out,
+                            Affine<P>* __restrict__ out, uint8_t* __restrict__ is_inf) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Xyzz<P> x = xyzz_from_jacobian<P>(in[i]);
+  Affine<P> a = xyzz_to_affine<P>(x);
+  const bool inf = xyzz_is_inf<P>(x);
+  if (!inf && !mont_out) {
+    a.x = fp_from_mont<P>(a.x);
+    a.y = fp_from_mont<P>(a.y);
+  }
+  out[i] = a;
+  is_inf[i] = inf ? 1 : 0;
+}
+
+template <class P>
+__global__ void k_test_fq(int op, const Fp<P>* __restrict__ a, const Fp<P>* __restrict__ b,
+                          Fp<P>* __restrict__ o, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Fp<P> x = a[i], y = b ? b[i] : fp_zero<P>(), r;
+  switch (op) {
+    case 0: r = fp_add<P>(x, y); break;
+    case 1: r = fp_sub<P>(x, y); break;
+    case 2: r = fp_mul<P>(x, y); break;
+    case 3: r = fp_sqr<P>(x); break;
+    case 4: r = fp_dbl<P>(x); break;
+    case 5: r = fp_to_mont<P>(x); break;
+    case 6: r = fp_from_mont<P>(x); break;
+    case 7: r = fp_inv<P>(x); break;
+    default: r = fp_neg<P>(x); break;
+  }
+  o[i] = r;
+}
+
+template <class P>
+__global__ void k_test_ec(int op, const Jacobian<P>* __restrict__ a, const void* __restrict__ b,
+                          Jacobian<P>* __restrict__ o, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Xyzz<P> x = xyzz_from_jacobian<P>(a[i]), r;
+  if (op == 0) {
+    r = xyzz_add<P>(x, xyzz_from_jacobian<P>(reinterpret_cast<const Jacobian<P>*>(b)[i]));
+  } else if (op == 1) {
+    Affine<P> q = reinterpret_cast<const Affine<P>*>(b)[i];
+    r = x;
+    if (!aff_is_identity<P>(q)) xyzz_madd<P>(r, q);
+  } else {
+    r = xyzz_dbl<P>(x);
+  }
+  o[i] = xyzz_to_jacobian<P>(r);
+}
+
+// --- synthetic inputs -------------------------------------------------------------------------
+MSM_HD uint64_t splitmix64(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+struct ScalarField {
+  uint32_t r[8];  // modulus, little-endian
+  uint32_t bits;
+};
+
+__global__ void k_synth_scalars(ScalarField fr, uint64_t seed, uint64_t start, uint32_t n,
+                                uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t top_mask = (fr.bits % 64) ? ((1ull << (fr.bits % 64)) - 1) : ~0ull;
+  uint64_t k[4];
+  for (uint64_t attempt = 0;; attempt++) {
+    const uint64_t s = seed + attempt * 0xD1B54A32D192ED03ull;
+#pragma unroll
+    for (int j = 0; j < 4; j++) k[j] = splitmix64(s, 4 * (start + i) + j);
+    k[3] &= top_mask;
+    // k < r ?
+    bool lt = false, decided = false;
+#pragma unroll
+    for (int j = 3; j >= 0; j--) {
+      const uint64_t rj = ((uint64_t)fr.r[2 * j + 1] << 32) | fr.r[2 * j];
+      if (!decided && k[j] != rj) {
+        lt = k[j] < rj;
+        decided = true;
+      }
+    }
+    if (lt) break;
+  }
+  uint4* o = reinterpret_cast<uint4*>(out) + 2 * (size_t)i;
+  o[0] = make_uint4((uint32_t)k[0], (uint32_t)(k[0] >> 32), (uint32_t)k[1], (uint32_t)(k[1] >> 32));
+  o[1] = make_uint4((uint32_t)k[2], (uint32_t)(k[2] >> 32), (uint32_t)k[3], (uint32_t)(k[3] >> 32));
+}
+
+// P_i = (a + (start+i) b) G.  Each thread produces RUN consecutive points: one double-and-add for
+// its first point, RUN-1 mixed additions of D = b*G, then one shared inversion (Montgomery's
+// trick) to normalise them.  gen / d are affine Montgomery.
+constexpr int SYNTH_RUN = 16;
+template <class P>
+__global__ void __launch_bounds__(64)
+k_synth_points(Affine<P> gen, Affine<P> d, uint64_t a, uint64_t b, uint64_t start, uint32_t n,
+               Affine<P>* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t i0 = (uint64_t)t * SYNTH_RUN;
+  if (i0 >= n) return;
+  const uint32_t cnt = (uint32_t)min((uint64_t)SYNTH_RUN, (uint64_t)n - i0);
+  // k = a + (start + i0) * b, up to 129 bits
+  const uint64_t m = start + i0;
+  const uint64_t lo = m * b, hi = __umul64hi(m, b);
+  uint64_t k0 = lo + a;
+  uint64_t c0 = k0 < lo ? 1 : 0;
+  uint64_t k1 = hi + c0;
+  uint64_t k2 = k1 < hi ? 1 : 0;
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (int bit = 128; bit >= 0; bit--) {
+    acc = xyzz_dbl<P>(acc);
+    const uint64_t word = bit >= 128 ? k2 : (bit >= 64 ? k1 : k0);
+    if ((word >> (bit & 63)) & 1) xyzz_madd<P>(acc, gen);
+  }
+  Xyzz<P> pts[SYNTH_RUN];
+  Fp<P> pref[SYNTH_RUN];
+  Fp<P> prod = fp_one<P>();
+  for (uint32_t j = 0; j < cnt; j++) {
+    pts[j] = acc;
+    pref[j] = prod;
+    prod = fp_mul<P>(prod, fp_mul<P>(acc.zz, acc.zzz));  // never infinity: k < group order
+    xyzz_madd<P>(acc, d);
+  }
+  Fp<P> inv = fp_inv<P>(prod);
+  for (int j = (int)cnt - 1; j >= 0; j--) {
+    Fp<P> zi = fp_mul<P>(inv, pref[j]);  // 1 / (zz*zzz)
+    inv = fp_mul<P>(inv, fp_mul<P>(pts[j].zz, pts[j].zzz));
+    Affine<P> o;
+    o.x = fp_mul<P>(pts[j].x, fp_mul<P>(zi, pts[j].zzz));
+    o.y = fp_mul<P>(pts[j].y, fp_mul<P>(zi, pts[j].zz));
+    store_vec(&out[i0 + j], o);
+  }
+}
+
+}  // namespace msm

@@ -1,0 +1,166 @@
+/* msm_b200.h -- C ABI of the B200-native MSM engine (libmsm_b200.so).
+ *
+ * The reference has no FFI on this path: its Rust host code reaches the device through
+ * rustacuda's cuLaunchKernel by mangled kernel name (ag-cuda-ec/src/multiexp.rs:57-72).  This
+ * header is therefore the boundary a thin Rust shim (rust/ in this repo) binds
+ * one level up, under the two host APIs that stay frozen:
+ *
+ *   ag_cuda_ec::{init_global_workspace, init_local_workspace}   ag-cuda-workspace-macro/src/lib.rs:58-78
+ *   ag_cuda_ec::multiexp::upload_multiexp_bases_{st,mt}          ag-cuda-ec/src/multiexp.rs:12-19
+ *   ag_cuda_ec::multiexp::multiple_multiexp_{st,mt}              ag-cuda-ec/src/multiexp.rs:22-81
+ *   ec_gpu_proxy::multiexp::MultiexpKernel::{create,create_with_abort,multiexp,num_kernels}
+ *                                                                ec-gpu-proxy/src/multiexp.rs:266-403
+ *
+ * Memory layouts (identical to the reference):
+ *   base point   {x, y}: 2 x N little-endian u32 limbs, Montgomery form (R = 2^(32N));
+ *                N = 8 (BN254, 64 B/point), N = 12 (BLS12-381, 96 B/point); identity = all zero
+ *                (GpuRepr for Affine, ag-types/src/impls.rs:48-58)
+ *   scalar       32 bytes little-endian, canonical (non-Montgomery) integer < r
+ *                (PrimeFieldRepr::to_bigint -> BigInt<4>, ag-types/src/impls.rs:7-18)
+ *   result point {x, y, z}: Jacobian, Montgomery form, infinity <=> z == 0
+ *                (POINT_jacobian, ag-build/cl/ec.cl:10-14).  Any representative of the group
+ *                element may be returned; callers compare as group elements / after into_affine()
+ *                (ag-cuda-ec/src/multiexp.rs:125, ec-gpu-proxy/tests/multiexp.rs:99).
+ *
+ * Conventions: every function returns 0 (MSM_OK) or an msm_status; no exceptions cross the
+ * boundary; every handle is owned by the caller and freed by the matching *_destroy / *_free.
+ * A context is not re-entrant: a second concurrent call on the same context returns
+ * MSM_ERR_BUSY, mirroring CudaError::ContextAlreadyInUse (ag-cuda-proxy/src/context.rs:20-27).
+ * Distinct contexts are independent (the reference's per-thread "_mt" workspaces).
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef MSM_B200_H
+#define MSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MSM_OK = 0,
+  MSM_ERR_INVALID = 1,     /* bad argument (null pointer, size mismatch, unknown curve) */
+  MSM_ERR_CUDA = 2,        /* CUDA runtime failure; msm_last_error() has the text (EcError::GpuTools) */
+  MSM_ERR_BUSY = 3,        /* context already in use (CudaError::ContextAlreadyInUse) */
+  MSM_ERR_ABORTED = 4,     /* abort flag observed (EcError::Aborted, ec-gpu-proxy/src/multiexp.rs:140-144) */
+  MSM_ERR_NO_DEVICE = 5,   /* "No working GPUs found!" (ec-gpu-proxy/src/multiexp.rs:305-307) */
+  MSM_ERR_TOO_LARGE = 6    /* sizes beyond the u32 index space the reference also assumes */
+} msm_status;
+
+typedef enum { MSM_CURVE_BN254_G1 = 0, MSM_CURVE_BLS12_381_G1 = 1 } msm_curve;
+
+typedef struct msm_ctx msm_ctx;     /* = CudaWorkspace / MultiexpKernel (one or more devices) */
+typedef struct msm_bases msm_bases; /* = DeviceData holding resident bases */
+
+/* Per-phase device times of the last call on device 0 of the context, milliseconds (CUDA events). */
+typedef struct {
+  float h2d_ms;        /* scalar upload */
+  float sort_ms;       /* digit decomposition + bucket sort */
+  float accumulate_ms; /* bucket accumulation (the IMAD-bound phase) */
+  float reduce_ms;     /* bucket reduction + window combine (+ cross-GPU gather) */
+  float total_ms;      /* first kernel to result ready */
+  uint32_t window_bits;
+  uint32_t num_windows;
+  uint64_t num_entries;   /* non-zero digits sorted */
+  uint64_t kernel_launches;
+} msm_timings;
+
+/* ---- contexts -------------------------------------------------------------------------- */
+/* Number of visible CUDA devices (<= 0: none). */
+int msm_device_count(void);
+/* Create a context over `n_devices` devices (device_ids == NULL: devices 0..n_devices-1;
+ * n_devices == 0: all visible devices).  Replaces CudaWorkspace::from_bytes
+ * (ag-cuda-proxy/src/module.rs:24-42) and MultiexpKernel::create
+ * (ec-gpu-proxy/src/multiexp.rs:266-322). */
+int msm_ctx_create(int curve, const int* device_ids, int n_devices, msm_ctx** out);
+int msm_ctx_destroy(msm_ctx* ctx);
+/* MultiexpKernel::num_kernels (ec-gpu-proxy/src/multiexp.rs:402). */
+int msm_ctx_num_devices(const msm_ctx* ctx);
+/* Cooperative cancel, polled between phases: replaces the maybe_abort callback of
+ * MultiexpKernel::create_with_abort.  flag may be NULL to clear. */
+int msm_set_abort_flag(msm_ctx* ctx, const volatile int* flag);
+/* Text of the last error on this context (or of context creation when ctx == NULL). */
+const char* msm_last_error(const msm_ctx* ctx);
+int msm_last_timings(const msm_ctx* ctx, msm_timings* out);
+/* Window-size override for experiments (0 = automatic).  Results never depend on it. */
+int msm_set_window_bits(msm_ctx* ctx, uint32_t c);
+
+/* ---- resident bases -------------------------------------------------------------------- */
+/* upload_multiexp_bases (ag-cuda-ec/src/multiexp.rs:12-19): copy n_points {x,y} Montgomery
+ * points from host memory to device 0 of the context and keep them resident. */
+int msm_bases_upload(msm_ctx* ctx, const void* xy_mont, size_t n_points, msm_bases** out);
+/* Same, but split contiguously over all devices of the context, ceil(n/devices) points each:
+ * the partition MultiexpKernel::parallel_multiexp uses (ec-gpu-proxy/src/multiexp.rs:329-337). */
+int msm_bases_upload_sharded(msm_ctx* ctx, const void* xy_mont, size_t n_points, msm_bases** out);
+/* Wrap points that already live in device memory of device 0 (no copy, not owned). */
+int msm_bases_wrap_device(msm_ctx* ctx, const void* d_xy_mont, size_t n_points, msm_bases** out);
+/* DeviceData::size (ag-cuda-proxy/src/params.rs:209): bytes. */
+size_t msm_bases_size_bytes(const msm_bases* b);
+size_t msm_bases_num_points(const msm_bases* b);
+int msm_bases_free(msm_bases* b);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* multiple_multiexp (ag-cuda-ec/src/multiexp.rs:22-81).  `scalars` = one row of L scalars in
+ * host memory; bases = num_lines * L resident points (num_lines = points / L).  Each line is cut
+ * into num_chunks chunks of L / num_chunks points; out_jacobian receives num_lines * num_chunks
+ * points, task (line, chunk) at index line * num_chunks + chunk (ag-build/cl/multiexp.cl:262):
+ *     out[line*num_chunks + chunk] = sum_{i in chunk} scalars[i] * bases[line*L + i].
+ * window_hint / neg_is_cheap are accepted for signature compatibility; the engine chooses its
+ * own signed-digit window and the result does not depend on them (reference test
+ * ag-cuda-ec/src/multiexp.rs:115-143).  Synchronous: the result is in out_jacobian on return. */
+int msm_multiple_multiexp(msm_ctx* ctx, const msm_bases* bases, const void* scalars, size_t L,
+                          uint32_t num_chunks, uint32_t window_hint, int neg_is_cheap,
+                          void* out_jacobian);
+/* Same with the scalar row and the result buffer in device memory of device 0 (no host copies;
+ * used for device-resident timing).  Returns after the result is complete. */
+int msm_multiple_multiexp_device(msm_ctx* ctx, const msm_bases* bases, const void* d_scalars,
+                                 size_t L, uint32_t num_chunks, void* d_out_jacobian);
+
+/* MultiexpKernel::multiexp (ec-gpu-proxy/src/multiexp.rs:372-400): one MSM over n host points
+ * and n host scalars (the Rust shim applies `skip` as a pointer offset), split over all devices
+ * of the context in contiguous chunks of ceil(n/devices); per-device partial points are gathered
+ * on device 0 over NVLink peer copies and summed there.  out_jacobian = one point. */
+int msm_multiexp(msm_ctx* ctx, const void* bases_xy_mont, const void* scalars, size_t n,
+                 void* out_jacobian);
+/* Same with bases resident from msm_bases_upload_sharded (or msm_bases_upload on a one-device
+ * context); uses bases[skip .. skip + n). */
+int msm_multiexp_resident(msm_ctx* ctx, const msm_bases* bases, size_t skip, const void* scalars,
+                          size_t n, void* out_jacobian);
+
+/* ---- small device-side helpers used by callers, tests and the bench ----------------------- */
+/* Sum `count` Jacobian points that live in device memory of device 0 into one Jacobian point
+ * (device memory): the on-device replacement of the host loop acc.add_assign(&r)
+ * (ec-gpu-proxy/src/multiexp.rs:394-397) after an NVLink / NCCL gather of per-GPU partials. */
+int msm_sum_points_device(msm_ctx* ctx, const void* d_jacobian, size_t count, void* d_out_jacobian);
+/* Jacobian -> affine {x,y} (Montgomery when mont_out != 0, else canonical) on the device, host
+ * buffers in/out; infinity -> (0,0) and out_is_inf[i] = 1.  Curve::into_affine. */
+int msm_to_affine(msm_ctx* ctx, const void* jacobian, size_t count, int mont_out, void* out_xy,
+                  uint8_t* out_is_inf);
+/* Deterministic synthetic inputs generated on the device (the counterpart of
+ * ag-cuda-ec/src/test_tools.rs:4-15 random_input).  Outputs are device pointers on device 0.
+ * points: P_i = (a + (start+i) b) G with 64-bit a, b derived from seed; scalars uniform < r. */
+int msm_synth_points_device(msm_ctx* ctx, uint64_t seed, size_t start, size_t n, void* d_xy_mont);
+int msm_synth_scalars_device(msm_ctx* ctx, uint64_t seed, size_t start, size_t n, void* d_scalars);
+/* Per-primitive known-answer kernels, the counterpart of ag-build/cl/test.cl:1-35.  Host buffers.
+ * fq op: 0 add, 1 sub, 2 mul, 3 sqr, 4 double, 5 to_mont, 6 from_mont, 7 inverse, 8 neg.
+ * ec op: 0 add(Jac a, Jac b), 1 mixed add(Jac a, Aff b), 2 double(Jac a). */
+int msm_test_fq_op(msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count);
+int msm_test_ec_op(msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count);
+
+/* Device memory helpers so that non-CUDA hosts (ctypes, Rust) can stage buffers on device 0. */
+int msm_device_alloc(msm_ctx* ctx, size_t bytes, void** d_ptr);
+int msm_device_free(msm_ctx* ctx, void* d_ptr);
+int msm_memcpy_h2d(msm_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int msm_memcpy_d2h(msm_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* Pin / unpin a host range so that scalar uploads run at full PCIe rate. */
+int msm_host_register(void* h_ptr, size_t bytes);
+int msm_host_unregister(void* h_ptr);
+
+const char* msm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSM_B200_H */

@@ -1,0 +1,255 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against the CPU oracle.
+
+Integer arithmetic only: the bar is bit-exact equality of the canonical affine coordinates
+(the reference compares after into_affine(), ec-gpu-proxy/tests/multiexp.rs:99).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from util import FQ, SEED, adversarial_inputs, assert_same_points
+
+pytestmark = pytest.mark.gpu
+
+CURVES = [0, 1]
+
+
+@pytest.fixture(scope="module")
+def ws(engine):
+    return {c: engine.Workspace(c) for c in CURVES}
+
+
+def _rand_fq(oracle, curve, n, rng):
+    p = int.from_bytes(oracle.constant(curve, 0).tobytes(), "little")
+    vals = [int.from_bytes(rng.bytes(FQ[curve] + 8), "little") % p for _ in range(n)]
+    vals[0], vals[1], vals[2] = 0, p - 1, 1
+    return np.frombuffer(b"".join(v.to_bytes(FQ[curve], "little") for v in vals), dtype=np.uint8).copy()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_field_ops(engine, oracle, ws, curve):
+    """Counterpart of ag-build/src/tests/test_fields.rs:11-107 (add, sub, mul, sqr, double, mont,
+    unmont) plus inverse / neg, 4096 samples per op instead of 10."""
+    lib = engine.load_library()
+    rng = np.random.default_rng(1234 + curve)
+    n = 4096
+    a, b = _rand_fq(oracle, curve, n, rng), _rand_fq(oracle, curve, n, rng)
+    for op in range(9):
+        aa = a.copy()
+        if op == 7:
+            aa[: FQ[curve]] = a[FQ[curve]: 2 * FQ[curve]]  # no inverse of zero
+        want = oracle.fq_op(curve, op, aa, b)
+        got = np.zeros_like(aa)
+        rc = lib.msm_test_fq_op(ws[curve].handle, op, aa.ctypes.data, b.ctypes.data, got.ctypes.data, n)
+        assert rc == 0
+        assert (got == want).all(), f"fq op {op} curve {curve}"
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_ec_ops(engine, oracle, ws, curve):
+    """Counterpart of ag-build/src/tests/test_ec.rs:7-37 for add / mixed add / double incl. the
+    exceptional cases (equal inputs, inverse inputs, infinity)."""
+    lib = engine.load_library()
+    n, fq = 512, FQ[curve]
+    pts = oracle.gen_points(curve, 7, n)
+    sc = oracle.gen_scalars(curve, 9, n)
+    jac = np.stack([oracle.scalar_mul(curve, pts[i], sc[i]) for i in range(n)])
+    jac2 = np.stack([oracle.scalar_mul(curve, pts[(i * 7 + 3) % n], sc[(i + 1) % n]) for i in range(n)])
+    jac2[0] = jac[0]
+    jac2[2] = 0
+    jac[3] = 0
+    one = oracle.constant(curve, 1)
+    lifted = np.zeros((n, 3 * fq), dtype=np.uint8)
+    lifted[:, : 2 * fq] = pts
+    lifted[:, 2 * fq:] = one
+    neg = pts.copy()
+    neg[:, fq:] = oracle.fq_op(curve, 8, pts[:, fq:].copy())
+    for op, a, b in ((0, jac, jac2), (1, jac, pts), (2, jac, None), (1, lifted, pts), (1, lifted, neg)):
+        want = oracle.ec_op(curve, op, a, b)
+        got = np.zeros_like(a)
+        rc = lib.msm_test_ec_op(ws[curve].handle, op, a.ctypes.data, None if b is None else b.ctypes.data,
+                                got.ctypes.data, n)
+        assert rc == 0
+        assert_same_points(oracle, curve, got, want, f"ec op {op}")
+
+
+def _synth(engine, ws, curve, n, seed=SEED, start=0):
+    """Device-generated inputs copied back to the host."""
+    lib = engine.load_library()
+    h = ws.handle
+    dp, ds = ctypes.c_void_p(), ctypes.c_void_p()
+    assert lib.msm_device_alloc(h, n * 2 * FQ[curve], ctypes.byref(dp)) == 0
+    assert lib.msm_device_alloc(h, n * 32, ctypes.byref(ds)) == 0
+    assert lib.msm_synth_points_device(h, seed, start, n, dp) == 0
+    assert lib.msm_synth_scalars_device(h, seed, start, n, ds) == 0
+    pts = np.zeros((n, 2 * FQ[curve]), dtype=np.uint8)
+    sc = np.zeros((n, 32), dtype=np.uint8)
+    assert lib.msm_memcpy_d2h(h, pts.ctypes.data, dp, pts.nbytes) == 0
+    assert lib.msm_memcpy_d2h(h, sc.ctypes.data, ds, sc.nbytes) == 0
+    lib.msm_device_free(h, dp)
+    lib.msm_device_free(h, ds)
+    return pts, sc
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_synthetic_inputs_match_oracle_generator(engine, oracle, ws, curve):
+    n = 5000
+    pts, sc = _synth(engine, ws[curve], curve, n, start=123)
+    assert (sc == oracle.gen_scalars(curve, SEED, n, start=123)).all()
+    assert (pts == oracle.gen_points(curve, SEED, n, start=123)).all()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("log_n", [0, 5, 10, 11, 14, 16])
+def test_multiexp_vs_cpu(engine, oracle, curve, log_n):
+    """ec-gpu-proxy/tests/multiexp.rs:38-105 (gpu_multiexp_consistency): MultiexpKernel::multiexp
+    == multiexp_cpu after into_affine; sizes 2^10, 2^11 as there, plus smaller and larger."""
+    n = 1 << log_n
+    pts = oracle.gen_points(curve, SEED, n)
+    sc = oracle.gen_scalars(curve, SEED, n)
+    kern = engine.MultiexpKernel.create([0], curve)
+    got = kern.multiexp(engine.Worker(), pts, sc, 0)
+    want = oracle.multiexp_cpu(curve, pts, sc)
+    assert_same_points(oracle, curve, got, want, f"n=2^{log_n}")
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_multiexp_skip_and_empty(engine, oracle, curve):
+    n = 300
+    pts = oracle.gen_points(curve, SEED, n + 17)
+    sc = oracle.gen_scalars(curve, SEED, n)
+    kern = engine.MultiexpKernel.create([0], curve)
+    got = kern.multiexp(engine.Worker(), pts, sc, 17)
+    want = oracle.multiexp_cpu(curve, pts[17:], sc)
+    assert_same_points(oracle, curve, got, want, "skip")
+    empty = kern.multiexp(engine.Worker(), pts, sc[:0], 0)
+    assert not empty[2 * FQ[curve]:].any()  # z == 0: infinity
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_multiple_multiexp_batch(engine, oracle, ws, curve):
+    """ag-cuda-ec/src/multiexp.rs:93-145 (test_multiexp_batch): 2 lines x 32 chunks x 64 points,
+    window_size 1..=9 x neg_is_cheap in {true,false}; every combination must give the same result
+    as the per-chunk CPU MSM."""
+    CHUNK, CHUNKS, LINES = 64, 32, 2
+    L = CHUNK * CHUNKS
+    pts = oracle.gen_points(curve, SEED + 1, L * LINES)
+    sc = oracle.gen_scalars(curve, SEED + 1, L)
+    bases_gpu = engine.upload_multiexp_bases(ws[curve], pts)
+    assert bases_gpu.size() == pts.nbytes
+    want = oracle.multiple_multiexp(curve, pts, sc, CHUNKS)
+    for window_size in range(1, 10):
+        for neg in (True, False):
+            got = engine.multiple_multiexp(ws[curve], bases_gpu, sc, CHUNKS, window_size, neg)
+            assert got.shape == want.shape
+            assert_same_points(oracle, curve, got, want, f"w={window_size} neg={neg}")
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("c", [2, 3, 5, 8, 11, 13, 16])
+def test_result_independent_of_engine_window(engine, oracle, ws, curve, c):
+    n = 3000
+    pts, sc = adversarial_inputs(oracle, curve, n)
+    w = ws[curve]
+    w.set_window_bits(c)
+    try:
+        bases_gpu = engine.upload_multiexp_bases(w, pts)
+        got = engine.multiple_multiexp(w, bases_gpu, sc, 1, 8, True)
+        assert w.timings()["window_bits"] == c
+    finally:
+        w.set_window_bits(0)
+    want = oracle.multiple_multiexp(curve, pts, sc, 1)
+    assert_same_points(oracle, curve, got, want, f"c={c}")
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_edge_cases(engine, oracle, ws, curve):
+    """Zero / one / r-1 scalars, identity bases, repeated bases, P and -P."""
+    n = 4096
+    pts, sc = adversarial_inputs(oracle, curve, n)
+    bases_gpu = engine.upload_multiexp_bases(ws[curve], pts)
+    for chunks in (1, 4, 64):
+        got = engine.multiple_multiexp(ws[curve], bases_gpu, sc, chunks, 8, True)
+        want = oracle.multiple_multiexp(curve, pts, sc, chunks)
+        assert_same_points(oracle, curve, got, want, f"adversarial chunks={chunks}")
+    # all-zero scalars -> infinity; all-identity bases -> infinity
+    z = np.zeros_like(sc)
+    got = engine.multiple_multiexp(ws[curve], bases_gpu, z, 2, 8, True)
+    assert not got[:, 2 * FQ[curve]:].any()
+    ident = engine.upload_multiexp_bases(ws[curve], np.zeros_like(pts))
+    got = engine.multiple_multiexp(ws[curve], ident, sc, 2, 8, True)
+    assert not got[:, 2 * FQ[curve]:].any()
+    # ragged: L not divisible by num_chunks drops the tail (ag-build/cl/multiexp.cl:235)
+    got = engine.multiple_multiexp(ws[curve], bases_gpu, sc, 3, 8, True)
+    want = oracle.multiple_multiexp(curve, pts, sc, 3)
+    assert_same_points(oracle, curve, got, want, "ragged")
+
+
+def test_bn254_batched_4096(engine, oracle, ws):
+    """Shape of ag-cuda-ec/benches/multiexp.rs:19-22,56 scaled down: 64 MSMs of 2^12 points."""
+    curve, chunks, cl = 0, 64, 4096
+    pts, sc = _synth(engine, ws[curve], curve, chunks * cl)
+    bases_gpu = engine.upload_multiexp_bases(ws[curve], pts)
+    got = engine.multiple_multiexp(ws[curve], bases_gpu, sc, chunks, 8, False)
+    want = oracle.multiple_multiexp(curve, pts, sc, chunks)
+    assert_same_points(oracle, curve, got, want, "64 x 4096")
+
+
+def test_bn254_2pow20_bit_exact(engine, oracle, ws):
+    """BASELINE.json configs[1]: BN254 G1 MSM 2^20 on one B200, bit-exact vs the CPU multiexp."""
+    curve, n = 0, 1 << 20
+    pts, sc = _synth(engine, ws[curve], curve, n)
+    kern = engine.MultiexpKernel.create([0], curve)
+    got = kern.multiexp(engine.Worker(), pts, sc, 0)
+    want = oracle.multiexp_cpu(curve, pts, sc)
+    assert_same_points(oracle, curve, got, want, "2^20")
+
+
+def test_linearity_at_full_size(engine, oracle, ws):
+    """Size-independent property at BASELINE's full size (2^24 would take the oracle minutes):
+    MSM(k, P) over [0, n) == MSM over [0, n/2) + MSM over [n/2, n), and MSM(k, P) with every
+    scalar replaced by r - k is the negation."""
+    curve, n = 0, 1 << 22
+    lib = engine.load_library()
+    w = ws[curve]
+    pts, sc = _synth(engine, w, curve, n)
+    bases_gpu = engine.upload_multiexp_bases(w, pts)
+    whole = engine.multiple_multiexp(w, bases_gpu, sc, 1, 8, True)
+    halves = engine.multiple_multiexp(w, bases_gpu, sc, 2, 8, True)
+    s = oracle.ec_op(curve, 0, halves[0:1].copy(), halves[1:2].copy())
+    assert_same_points(oracle, curve, whole, s, "halves")
+    r = int.from_bytes(oracle.constant(curve, 5).tobytes(), "little")
+    # negate the first 1000 scalars only (python big ints), check the partial identity on a sub-MSM
+    m = 1000
+    neg = sc[:m].copy()
+    for i in range(m):
+        k = int.from_bytes(sc[i].tobytes(), "little")
+        neg[i] = np.frombuffer(((r - k) % r).to_bytes(32, "little"), dtype=np.uint8)
+    sub = engine.upload_multiexp_bases(w, pts[:m])
+    a = engine.multiple_multiexp(w, sub, sc[:m], 1, 8, True)
+    b = engine.multiple_multiexp(w, sub, neg, 1, 8, True)
+    tot = oracle.ec_op(curve, 0, a.copy(), b.copy())
+    assert oracle.to_affine(curve, tot)[1].all()
+    del lib
+
+
+def test_context_busy_and_errors(engine, oracle):
+    """A context is not re-entrant (CudaError::ContextAlreadyInUse, ag-cuda-proxy/src/context.rs:20-27);
+    invalid arguments are reported, not crashed on."""
+    lib = engine.load_library()
+    w = engine.Workspace(0)
+    assert lib.msm_multiple_multiexp(w.handle, None, None, 0, 1, 8, 1, None) != 0
+    pts = oracle.gen_points(0, 1, 64)
+    bases_gpu = engine.upload_multiexp_bases(w, pts)
+    with pytest.raises(engine.CudaError):
+        engine.multiple_multiexp(w, bases_gpu, oracle.gen_scalars(0, 1, 128), 1, 8, True)  # L > bases
+    flag = ctypes.c_int(1)
+    kern = engine.MultiexpKernel.create([0], 0)
+    lib.msm_set_abort_flag(kern.workspace.handle, ctypes.addressof(flag))
+    with pytest.raises(engine.EcErrorAborted):
+        kern.multiexp(engine.Worker(), pts, oracle.gen_scalars(0, 1, 64), 0)
+    lib.msm_set_abort_flag(kern.workspace.handle, None)
+    kern2 = engine.MultiexpKernel.create_with_abort([0], lambda: True, 0)
+    with pytest.raises(engine.EcErrorAborted):
+        kern2.multiexp(engine.Worker(), pts, oracle.gen_scalars(0, 1, 64), 0)
