@@ -110,14 +110,18 @@ def load_library() -> ctypes.CDLL:
         "msm_last_error": ([vp], ctypes.c_char_p),
         "msm_last_timings": ([vp, ctypes.POINTER(Timings)], i32),
         "msm_set_window_bits": ([vp, u32], i32),
+        "msm_field_impl": ([vp], ctypes.c_char_p),
         "msm_bases_upload": ([vp, vp, sz, pp], i32),
         "msm_bases_upload_sharded": ([vp, vp, sz, pp], i32),
-        "msm_bases_wrap_device": ([vp, vp, sz, pp], i32),
+        "msm_bases_from_device": ([vp, vp, sz, pp], i32),
         "msm_bases_size_bytes": ([vp], sz),
         "msm_bases_num_points": ([vp], sz),
         "msm_bases_free": ([vp], i32),
         "msm_multiple_multiexp": ([vp, vp, vp, sz, u32, u32, i32, vp], i32),
         "msm_multiple_multiexp_device": ([vp, vp, vp, sz, u32, vp], i32),
+        "msm_multiple_multiexp_device_timed": ([vp, vp, vp, sz, u32, vp, u32, ctypes.POINTER(ctypes.c_float),
+                                                ctypes.POINTER(ctypes.c_float)], i32),
+        "msm_set_stream": ([vp, vp], i32),
         "msm_multiexp": ([vp, vp, vp, sz, vp], i32),
         "msm_multiexp_resident": ([vp, vp, sz, vp, sz, vp], i32),
         "msm_sum_points_device": ([vp, vp, sz, vp], i32),

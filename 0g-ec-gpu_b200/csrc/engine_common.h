@@ -1,0 +1,133 @@
+// engine_common.h -- host-side structures shared by engine.cu (C ABI) and the per-field
+// instantiation units (inst_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/msm_b200.h"
+
+namespace msm {
+
+// Grow-only device arena: replaces the per-call cuMemAlloc of the reference runtime
+// (ag-cuda-proxy/src/params.rs:58-78, ag-cuda-ec/src/multiexp.rs:42-44).
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  cudaError_t ensure(size_t bytes) {
+    off = 0;
+    if (bytes <= cap) return cudaSuccess;
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc((void**)&base, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc((void**)&base, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T> T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+  static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = off = 0;
+  }
+};
+
+struct DeviceCtx {
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  Arena arena;        // per-call scratch (sorted entries, buckets, partials)
+  Arena io;           // scalars / bases staged from the host + result points
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t launches = 0;
+  void* small = nullptr;  // 64 KiB persistent (partial-point gather)
+};
+
+struct FieldOps;
+
+}  // namespace msm
+
+struct msm_ctx {
+  int curve = 0;
+  const msm::FieldOps* ops = nullptr;
+  std::vector<msm::DeviceCtx> devs;
+  std::atomic<int> in_use{0};
+  const volatile int* abort_flag = nullptr;
+  std::string err;
+  msm_timings tm{};
+  uint32_t window_override = 0;
+};
+
+struct msm_bases {
+  msm_ctx* ctx = nullptr;
+  size_t n = 0;
+  struct Shard {
+    int dev_idx;
+    void* ptr;  // resident copy in the field's packed layout
+    size_t start, n;
+    bool owned;
+  };
+  std::vector<Shard> shards;
+};
+
+namespace msm {
+
+inline void set_error(msm_ctx* ctx, const std::string& s);
+extern thread_local std::string g_create_error;
+inline void set_error(msm_ctx* ctx, const std::string& s) {
+  if (ctx) ctx->err = s;
+  else g_create_error = s;
+}
+inline bool aborted(msm_ctx* ctx) { return ctx->abort_flag && *ctx->abort_flag; }
+inline uint32_t scalar_bits(int curve) { return curve == MSM_CURVE_BN254_G1 ? 254 : 255; }
+
+#define CU_TRY(ctx, call)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::msm::set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(_e));            \
+      return MSM_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+// Per-field entry points (one instantiation unit each, see engine_impl.cuh).
+struct FieldOps {
+  const char* name;
+  size_t api_point_bytes;     // {x,y} at the API boundary
+  size_t packed_point_bytes;  // resident copy
+  int (*multiple_multiexp)(msm_ctx*, const msm_bases*, const void* scalars, size_t L, uint32_t num_chunks,
+                           void* out, bool device_io);
+  int (*multiexp)(msm_ctx*, const void* host_bases, const msm_bases* resident, size_t skip, const void* scalars,
+                  size_t n, void* out);
+  // d_api (device, API layout) -> d_packed (device, resident layout); enqueued on dc.stream
+  int (*convert_bases)(msm_ctx*, DeviceCtx&, const void* d_api, size_t n, void* d_packed);
+  int (*synth_points)(msm_ctx*, uint64_t seed, size_t start, size_t n, void* d_out);
+  int (*test_fq)(msm_ctx*, int op, const void* a, const void* b, void* out, size_t count);
+  int (*test_ec)(msm_ctx*, int op, const void* a, const void* b, void* out, size_t count);
+  int (*to_affine)(msm_ctx*, const void* jac, size_t count, int mont_out, void* out_xy, uint8_t* out_inf);
+  int (*sum_points)(msm_ctx*, const void* d_in, size_t count, void* d_out);
+};
+const FieldOps* field_ops_bn254_u29();
+const FieldOps* field_ops_bn254_sat();
+const FieldOps* field_ops_bls381_sat();
+
+}  // namespace msm

@@ -1,0 +1,504 @@
+// engine_impl.cuh -- launch sequencing of the MSM pipeline, templated on the field class.
+// Instantiated once per (curve, field implementation) in inst_*.cu and reached from the C ABI
+// (engine.cu) through the FieldOps table.
+//
+// Replaces the host wrapper ag_cuda_ec::multiple_multiexp (ag-cuda-ec/src/multiexp.rs:22-81) and
+// the per-device part of ec_gpu_proxy::MultiexpKernel (ec-gpu-proxy/src/multiexp.rs:135-253,
+// 324-400).  Differences that are the point of the rewrite: no per-call cuMemAlloc, no per-call
+// function lookup or stream creation, window combine and cross-device sum on the device.
+#pragma once
+#include <type_traits>
+
+#include "engine_common.h"
+#include "kernels.cuh"
+
+namespace msm {
+
+// ---------------------------------------------------------------------------------------------
+// Window choice: minimise  W * (chunk_len * M_madd + 2^(c-1) * (2 * M_add + overhead))  in field
+// multiplies (M_madd = 10, M_add = 14), subject to the bucket array staying modest.  The
+// reference leaves this to the caller (window_size argument) or to calc_window_size
+// (ec-gpu-proxy/src/multiexp.rs:245-252); results never depend on it.
+// ---------------------------------------------------------------------------------------------
+inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_tasks_lines, size_t xyzz_bytes) {
+  double best = 1e300;
+  uint32_t best_c = 2;
+  for (uint32_t c = 2; c <= 22; c++) {
+    const uint32_t W = (bits + 1 + c - 1) / c;
+    const double B = (double)(1u << (c - 1));
+    const double bucket_bytes = (double)n_tasks_lines * W * B * (double)xyzz_bytes;
+    if (bucket_bytes > 6e9) break;
+    const double cost = (double)W * ((double)chunk_len * 10.0 + B * (2.0 * 14.0 + 6.0));
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+struct Plan {
+  Geometry geo;
+  uint32_t n_lines, S, n_slices, Q, RW, PG, n_tasks;
+  uint64_t E_max;
+  size_t scratch_bytes;
+};
+
+template <class F>
+int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, Plan& pl) {
+  if (L == 0 || num_chunks == 0 || n_lines == 0 || num_chunks > L) return MSM_ERR_INVALID;
+  Geometry& g = pl.geo;
+  g.num_chunks = num_chunks;
+  g.chunk_len = L / num_chunks;  // tail dropped, as ag-build/cl/multiexp.cl:235
+  g.L = g.chunk_len * num_chunks;
+  g.scalar_bits = scalar_bits(ctx->curve);
+  uint32_t c = ctx->window_override;
+  if (const char* env = getenv("MSM_B200_WINDOW")) {
+    if (!c) c = (uint32_t)atoi(env);
+  }
+  if (c < 2 || c > 24) c = choose_window(g.chunk_len, g.scalar_bits, (uint64_t)num_chunks * n_lines, sizeof(Xyzz<F>));
+  g.c = c;
+  g.W = (g.scalar_bits + 1 + c - 1) / c;
+  g.B = 1u << (c - 1);
+  const uint64_t NB = (uint64_t)num_chunks * g.W * g.B;
+  if (NB >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
+  g.NB = (uint32_t)NB;
+  pl.n_lines = n_lines;
+  pl.n_tasks = n_lines * num_chunks;
+  pl.E_max = (uint64_t)g.L * g.W;
+  if (pl.E_max >= (1ull << 32) || (uint64_t)L * n_lines >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
+  // slice length: enough slices to fill the machine several times over, few cut buckets
+  uint32_t S = (uint32_t)(pl.E_max / (148ull * 512 * 8));
+  if (const char* env = getenv("MSM_B200_SLICE")) S = (uint32_t)atoi(env);
+  S = S < 8 ? 8 : (S > 1024 ? 1024 : S);
+  pl.S = S;
+  pl.n_slices = (uint32_t)((pl.E_max + S - 1) / S);
+  pl.Q = g.B < 8 ? g.B : 8;
+  const uint32_t TG = g.B / pl.Q;
+  pl.RW = TG < 128 ? TG : 128;
+  pl.PG = TG / pl.RW;
+  const uint32_t n_tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
+  size_t b = 0;
+  b += Arena::padded((size_t)(g.NB + 1) * 4) * 3;                            // counts, bucket_start, cursor
+  b += Arena::padded((size_t)(n_tiles + 1) * 4);                             // tile sums + grand total
+  b += Arena::padded(pl.E_max * 4);                                          // entries
+  b += Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));              // bucket accumulators
+  b += Arena::padded((size_t)2 * pl.n_slices * n_lines * sizeof(Xyzz<F>));   // slice partials
+  b += Arena::padded((size_t)pl.n_tasks * g.W * pl.PG * sizeof(Xyzz<F>));    // group partials
+  pl.scratch_bytes = b;
+  return MSM_OK;
+}
+
+// Enqueue one whole MSM batch on dc.stream.  d_scalars / d_out are device pointers.  No sync.
+template <class F>
+int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<F>* d_bases,
+                uint32_t line_stride, const uint32_t* d_scalars, ApiJacobian<F>* d_out, bool timed) {
+  const Geometry& g = pl.geo;
+  CU_TRY(ctx, dc.arena.ensure(pl.scratch_bytes));
+  const uint32_t n_tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
+  uint32_t* counts = dc.arena.take<uint32_t>(g.NB + 1);
+  uint32_t* bucket_start = dc.arena.take<uint32_t>(g.NB + 1);
+  uint32_t* cursor = dc.arena.take<uint32_t>(g.NB + 1);
+  uint32_t* tile_sums = dc.arena.take<uint32_t>(n_tiles + 1);
+  uint32_t* entries = dc.arena.take<uint32_t>(pl.E_max);
+  Xyzz<F>* bucket_acc = dc.arena.take<Xyzz<F>>((size_t)g.NB * pl.n_lines);
+  Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * pl.n_slices * pl.n_lines);
+  Xyzz<F>* group_partials = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * g.W * pl.PG);
+  cudaStream_t st = dc.stream;
+
+  if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
+  // --- sort: histogram, scan, scatter
+  CU_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.NB + 1) * 4, st));
+  const uint32_t db = 256, dg = (g.L + db - 1) / db;
+  k_digits<false><<<dg, db, 0, st>>>(d_scalars, g, counts, nullptr);
+  k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
+  k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
+  k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(bucket_start, g.NB, tile_sums, tile_sums + n_tiles, cursor);
+  k_digits<true><<<dg, db, 0, st>>>(d_scalars, g, cursor, entries);
+  if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
+  if (aborted(ctx)) return MSM_ERR_ABORTED;
+  // --- accumulate
+  {
+    const uint32_t tb = 128;
+    dim3 grid((pl.n_slices + tb - 1) / tb, pl.n_lines);
+    k_accumulate<F><<<grid, tb, 0, st>>>(d_bases, line_stride, entries, bucket_start, g.NB,
+                                         bucket_start + g.NB, pl.S, pl.n_slices, bucket_acc, partials);
+    dim3 fgrid((g.NB + tb - 1) / tb, pl.n_lines);
+    k_fixup<F><<<fgrid, tb, 0, st>>>(bucket_start, g.NB, pl.S, pl.n_slices, bucket_acc, partials);
+  }
+  if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[3], st));
+  if (aborted(ctx)) return MSM_ERR_ABORTED;
+  // --- reduce + combine
+  {
+    const uint32_t tb = 128;
+    const uint64_t n_threads = (uint64_t)g.NB * pl.n_lines / pl.Q;
+    k_bucket_reduce<F><<<(uint32_t)((n_threads + tb - 1) / tb), tb, tb * sizeof(Xyzz<F>), st>>>(
+        bucket_acc, (uint32_t)n_threads, g.B, pl.Q, pl.RW, group_partials);
+    const uint32_t wt = g.W < 32 ? 32 : (g.W > 256 ? 256 : ((g.W + 31) / 32) * 32);
+    k_window_combine<F><<<pl.n_tasks, wt, (size_t)g.W * sizeof(Xyzz<F>), st>>>(group_partials, g.W, pl.PG, g.c, d_out);
+  }
+  if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[4], st));
+  dc.launches += 10;
+  CU_TRY(ctx, cudaGetLastError());
+  return MSM_OK;
+}
+
+inline void collect_timings(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, bool have_h2d) {
+  msm_timings& t = ctx->tm;
+  memset(&t, 0, sizeof(t));
+  if (have_h2d) cudaEventElapsedTime(&t.h2d_ms, dc.ev[0], dc.ev[1]);
+  cudaEventElapsedTime(&t.sort_ms, dc.ev[1], dc.ev[2]);
+  cudaEventElapsedTime(&t.accumulate_ms, dc.ev[2], dc.ev[3]);
+  cudaEventElapsedTime(&t.reduce_ms, dc.ev[3], dc.ev[4]);
+  cudaEventElapsedTime(&t.total_ms, dc.ev[1], dc.ev[4]);
+  t.window_bits = pl.geo.c;
+  t.num_windows = pl.geo.W;
+  t.num_entries = pl.E_max;
+  t.kernel_launches = dc.launches;
+}
+
+template <class F>
+int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* scalars, size_t L,
+                           uint32_t num_chunks, void* out, bool device_io) {
+  if (bases->shards.size() != 1 || bases->shards[0].dev_idx != 0) {
+    set_error(ctx, "multiple_multiexp needs bases resident on device 0 (msm_bases_upload)");
+    return MSM_ERR_INVALID;
+  }
+  if (L == 0 || L > bases->n || L >= (1ull << 31)) {
+    set_error(ctx, "multiple_multiexp: exponent count must be in 1..=number of bases");
+    return MSM_ERR_INVALID;
+  }
+  const uint32_t n_lines = (uint32_t)(bases->n / L);  // ag-cuda-ec/src/multiexp.rs:28-30
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  Plan pl;
+  int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl);
+  if (rc) return rc;
+  if (aborted(ctx)) return MSM_ERR_ABORTED;
+  const uint32_t* d_scalars;
+  ApiJacobian<F>* d_out;
+  const size_t out_bytes = (size_t)pl.n_tasks * sizeof(ApiJacobian<F>);
+  if (device_io) {
+    d_scalars = static_cast<const uint32_t*>(scalars);
+    d_out = static_cast<ApiJacobian<F>*>(out);
+  } else {
+    CU_TRY(ctx, dc.io.ensure(Arena::padded(L * 32) + Arena::padded(out_bytes)));
+    uint32_t* ds = dc.io.take<uint32_t>(L * 8);
+    d_out = dc.io.take<ApiJacobian<F>>(pl.n_tasks);
+    CU_TRY(ctx, cudaEventRecord(dc.ev[0], dc.stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ds, scalars, L * 32, cudaMemcpyHostToDevice, dc.stream));
+    d_scalars = ds;
+  }
+  rc = enqueue_msm<F>(ctx, dc, pl, static_cast<const PackedAffine<F>*>(bases->shards[0].ptr), (uint32_t)L,
+                      d_scalars, d_out, true);
+  if (rc) {
+    cudaStreamSynchronize(dc.stream);
+    return rc;
+  }
+  if (!device_io) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, dc.stream));
+  CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  collect_timings(ctx, dc, pl, !device_io);
+  return MSM_OK;
+}
+
+template <class F>
+int convert_bases_impl(msm_ctx* ctx, DeviceCtx& dc, const void* d_api, size_t n, void* d_packed) {
+  if (n == 0) return MSM_OK;
+  k_convert_bases<F><<<(uint32_t)((n + 127) / 128), 128, 0, dc.stream>>>(
+      static_cast<const ApiAffine<F>*>(d_api), (uint32_t)n, static_cast<PackedAffine<F>*>(d_packed));
+  dc.launches += 1;
+  CU_TRY(ctx, cudaGetLastError());
+  return MSM_OK;
+}
+
+// One MSM split over all devices of the context (MultiexpKernel::multiexp).  Either host bases
+// (uploaded and converted per call, as the reference uploads per call) or resident sharded bases.
+template <class F>
+int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* resident, size_t skip,
+                  const void* scalars, size_t n, void* out) {
+  const size_t n_dev = ctx->devs.size();
+  if (n >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
+  if (n == 0) {
+    ApiJacobian<F> inf;
+    F::to_api(F::zero(), inf.x);
+    F::to_api(F::one(), inf.y);
+    F::to_api(F::zero(), inf.z);
+    memcpy(out, &inf, sizeof(inf));
+    return MSM_OK;
+  }
+  struct Job {
+    size_t dev_idx;
+    const void* d_bases;  // resident (packed) device pointer
+    const char* h_bases;  // host pointer (API layout) when not resident
+    size_t s_off, cnt;
+  };
+  std::vector<Job> jobs;
+  if (resident) {
+    if (skip + n > resident->n) return MSM_ERR_INVALID;
+    for (const auto& sh : resident->shards) {
+      const size_t lo = std::max(skip, sh.start), hi = std::min(skip + n, sh.start + sh.n);
+      if (lo >= hi) continue;
+      jobs.push_back({(size_t)sh.dev_idx,
+                      static_cast<const char*>(sh.ptr) + (lo - sh.start) * sizeof(PackedAffine<F>), nullptr,
+                      lo - skip, hi - lo});
+    }
+  } else {
+    const size_t chunk = (n + n_dev - 1) / n_dev;  // ec-gpu-proxy/src/multiexp.rs:329-337
+    for (size_t d = 0; d * chunk < n; d++) {
+      const size_t cnt = std::min(chunk, n - d * chunk);
+      jobs.push_back({d, nullptr, static_cast<const char*>(host_bases) + d * chunk * sizeof(ApiAffine<F>),
+                      d * chunk, cnt});
+    }
+  }
+  std::vector<int> rcs(jobs.size(), MSM_OK);
+  std::vector<std::string> errs(jobs.size());
+  std::vector<Plan> plans(jobs.size());
+  std::vector<ApiJacobian<F>*> d_partials(jobs.size(), nullptr);
+  auto run_job = [&](size_t j) {
+    const Job& job = jobs[j];
+    DeviceCtx& dc = ctx->devs[job.dev_idx];
+    auto fail = [&](cudaError_t e, const char* what) {
+      errs[j] = std::string(what) + ": " + cudaGetErrorString(e);
+      rcs[j] = MSM_ERR_CUDA;
+    };
+    cudaError_t e = cudaSetDevice(dc.dev);
+    if (e != cudaSuccess) return fail(e, "cudaSetDevice");
+    msm_ctx shadow;  // per-thread error sink (ctx->err is not thread-safe)
+    shadow.curve = ctx->curve;
+    shadow.window_override = ctx->window_override;
+    shadow.abort_flag = ctx->abort_flag;
+    int rc = make_plan<F>(&shadow, (uint32_t)job.cnt, 1, 1, plans[j]);
+    if (rc) {
+      rcs[j] = rc;
+      return;
+    }
+    const size_t api_bytes = job.h_bases ? job.cnt * sizeof(ApiAffine<F>) : 0;
+    const size_t packed_bytes = job.h_bases ? job.cnt * sizeof(PackedAffine<F>) : 0;
+    e = dc.io.ensure(Arena::padded(job.cnt * 32) + Arena::padded(sizeof(ApiJacobian<F>)) +
+                     Arena::padded(api_bytes) + Arena::padded(packed_bytes));
+    if (e != cudaSuccess) return fail(e, "io arena");
+    uint32_t* ds = dc.io.take<uint32_t>(job.cnt * 8);
+    ApiJacobian<F>* d_out = dc.io.take<ApiJacobian<F>>(1);
+    const PackedAffine<F>* d_bases = static_cast<const PackedAffine<F>*>(job.d_bases);
+    cudaEventRecord(dc.ev[0], dc.stream);
+    if (job.h_bases) {
+      ApiAffine<F>* da = dc.io.take<ApiAffine<F>>(job.cnt);
+      PackedAffine<F>* dp = dc.io.take<PackedAffine<F>>(job.cnt);
+      e = cudaMemcpyAsync(da, job.h_bases, api_bytes, cudaMemcpyHostToDevice, dc.stream);
+      if (e != cudaSuccess) return fail(e, "bases H2D");
+      rc = convert_bases_impl<F>(&shadow, dc, da, job.cnt, dp);
+      if (rc) {
+        rcs[j] = rc;
+        errs[j] = shadow.err;
+        return;
+      }
+      d_bases = dp;
+    }
+    e = cudaMemcpyAsync(ds, static_cast<const char*>(scalars) + job.s_off * 32, job.cnt * 32,
+                        cudaMemcpyHostToDevice, dc.stream);
+    if (e != cudaSuccess) return fail(e, "scalars H2D");
+    rc = enqueue_msm<F>(&shadow, dc, plans[j], d_bases, (uint32_t)job.cnt, ds, d_out, true);
+    if (rc) {
+      rcs[j] = rc;
+      errs[j] = shadow.err;
+      cudaStreamSynchronize(dc.stream);
+      return;
+    }
+    d_partials[j] = d_out;
+  };
+  if (jobs.size() == 1) {
+    run_job(0);
+  } else {
+    // one host thread per device, as parallel_multiexp does (ec-gpu-proxy/src/multiexp.rs:346)
+    std::vector<std::thread> th;
+    for (size_t j = 0; j < jobs.size(); j++) th.emplace_back(run_job, j);
+    for (auto& t : th) t.join();
+  }
+  for (size_t j = 0; j < jobs.size(); j++) {
+    if (rcs[j] != MSM_OK) {  // first error wins (ec-gpu-proxy/src/multiexp.rs:351-364)
+      for (auto& job : jobs) {
+        cudaSetDevice(ctx->devs[job.dev_idx].dev);
+        cudaStreamSynchronize(ctx->devs[job.dev_idx].stream);
+      }
+      set_error(ctx, errs[j]);
+      return rcs[j];
+    }
+  }
+  // gather the per-device partial points on device 0 over peer copies, sum there: the on-device
+  // replacement of the host loop at ec-gpu-proxy/src/multiexp.rs:394-397
+  DeviceCtx& d0 = ctx->devs[0];
+  for (size_t j = 0; j < jobs.size(); j++) {
+    DeviceCtx& dc = ctx->devs[jobs[j].dev_idx];
+    CU_TRY(ctx, cudaSetDevice(dc.dev));
+    CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  }
+  CU_TRY(ctx, cudaSetDevice(d0.dev));
+  if (jobs.size() == 1 && jobs[0].dev_idx == 0) {
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_partials[0], sizeof(ApiJacobian<F>), cudaMemcpyDeviceToHost, d0.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(d0.stream));
+  } else {
+    ApiJacobian<F>* gather = reinterpret_cast<ApiJacobian<F>*>(d0.small);
+    ApiJacobian<F>* d_result = gather + jobs.size();
+    for (size_t j = 0; j < jobs.size(); j++) {
+      DeviceCtx& dc = ctx->devs[jobs[j].dev_idx];
+      if (dc.dev == d0.dev) {
+        CU_TRY(ctx, cudaMemcpyAsync(gather + j, d_partials[j], sizeof(ApiJacobian<F>), cudaMemcpyDeviceToDevice, d0.stream));
+      } else {
+        CU_TRY(ctx, cudaMemcpyPeerAsync(gather + j, d0.dev, d_partials[j], dc.dev, sizeof(ApiJacobian<F>), d0.stream));
+      }
+    }
+    k_sum_points<F><<<1, 32, 0, d0.stream>>>(gather, (uint32_t)jobs.size(), d_result);
+    d0.launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_result, sizeof(ApiJacobian<F>), cudaMemcpyDeviceToHost, d0.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(d0.stream));
+  }
+  for (size_t j = 0; j < jobs.size(); j++)
+    if (jobs[j].dev_idx == 0) collect_timings(ctx, d0, plans[j], true);
+  return MSM_OK;
+}
+
+// canonical generator in the API layout (Montgomery), computed with the host build of the field
+template <class F> ApiAffine<F> host_generator_api() {
+  uint32_t gx[F::API_WORDS] = {0}, gy[F::API_WORDS] = {0};
+  if (F::API_WORDS == 8) {  // BN254 G1: (1, 2)
+    gx[0] = 1;
+    gy[0] = 2;
+  } else {  // BLS12-381 G1
+    const uint32_t x[12] = {0xdb22c6bbu, 0xfb3af00au, 0xf97a1aefu, 0x6c55e83fu, 0x171bac58u, 0xa14e3a3fu,
+                            0x9774b905u, 0xc3688c4fu, 0x4fa9ac0fu, 0x2695638cu, 0x3197d794u, 0x17f1d3a7u};
+    const uint32_t y[12] = {0x46c5e7e1u, 0x0caa2329u, 0xa2888ae4u, 0xd03cc744u, 0x2c04b3edu, 0x00db18cbu,
+                            0xd5d00af6u, 0xfcf5e095u, 0x741d8ae4u, 0xa09e30edu, 0xe3aaa0f1u, 0x08b3f481u};
+    for (int i = 0; i < F::API_WORDS; i++) {
+      gx[i] = x[i];
+      gy[i] = y[i];
+    }
+  }
+  // integer -> API Montgomery form: multiply the "value whose API form is the integer" by R
+  using Sat = FieldSat<typename std::conditional<F::API_WORDS == 8, Bn254Fq, Bls381Fq>::type>;
+  ApiAffine<F> g;
+  typename Sat::Elem ex, ey;
+  for (int i = 0; i < F::API_WORDS; i++) {
+    ex.v[i] = gx[i];
+    ey.v[i] = gy[i];
+  }
+  ex = fp_to_mont<typename std::conditional<F::API_WORDS == 8, Bn254Fq, Bls381Fq>::type>(ex);
+  ey = fp_to_mont<typename std::conditional<F::API_WORDS == 8, Bn254Fq, Bls381Fq>::type>(ey);
+  for (int i = 0; i < F::API_WORDS; i++) {
+    g.x[i] = ex.v[i];
+    g.y[i] = ey.v[i];
+  }
+  return g;
+}
+
+template <class F> int synth_points_impl(msm_ctx* ctx, uint64_t seed, size_t start, size_t n, void* d_out) {
+  if (n == 0) return MSM_OK;
+  if (n >= (1ull << 32)) return MSM_ERR_TOO_LARGE;
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const uint64_t a = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ull, 0);
+  const uint64_t b = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ull, 1) | 1;
+  // D = b*G on the host (64 doublings; setup only)
+  const ApiAffine<F> gen_api = host_generator_api<F>();
+  const Affine<F> gen = affine_from_api<F>(&gen_api);
+  Xyzz<F> acc = xyzz_inf<F>();
+  for (int bit = 63; bit >= 0; bit--) {
+    acc = xyzz_dbl<F>(acc);
+    if ((b >> bit) & 1) xyzz_madd<F>(acc, gen);
+  }
+  ApiAffine<F> d_api;
+  xyzz_to_api_affine<F>(acc, true, &d_api);
+  const uint32_t threads = (uint32_t)((n + SYNTH_RUN - 1) / SYNTH_RUN);
+  k_synth_points<F><<<(threads + 63) / 64, 64, 0, dc.stream>>>(gen_api, d_api, a, b, (uint64_t)start, (uint32_t)n,
+                                                              static_cast<ApiAffine<F>*>(d_out));
+  dc.launches += 1;
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  return MSM_OK;
+}
+
+template <class F>
+int test_fq_impl(msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const size_t bytes = count * sizeof(ApiElem<F>);
+  CU_TRY(ctx, dc.io.ensure(3 * Arena::padded(bytes)));
+  ApiElem<F>* da = dc.io.take<ApiElem<F>>(count);
+  ApiElem<F>* db = dc.io.take<ApiElem<F>>(count);
+  ApiElem<F>* dout = dc.io.take<ApiElem<F>>(count);
+  CU_TRY(ctx, cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, dc.stream));
+  if (b) CU_TRY(ctx, cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, dc.stream));
+  using SatP = typename std::conditional<F::API_WORDS == 8, Bn254Fq, Bls381Fq>::type;
+  ApiElem<F> r2;
+  for (int i = 0; i < F::API_WORDS; i++) r2.w[i] = SatP::R2(i);
+  k_test_fq<F><<<(uint32_t)((count + 127) / 128), 128, 0, dc.stream>>>(op, da, b ? db : nullptr, r2, dout, (uint32_t)count);
+  dc.launches += 1;
+  CU_TRY(ctx, cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, dc.stream));
+  CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  return MSM_OK;
+}
+
+template <class F>
+int test_ec_impl(msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const size_t ja = count * sizeof(ApiJacobian<F>);
+  const size_t bb = op == 0 ? ja : (op == 1 ? count * sizeof(ApiAffine<F>) : 0);
+  CU_TRY(ctx, dc.io.ensure(3 * Arena::padded(ja)));
+  ApiJacobian<F>* da = dc.io.take<ApiJacobian<F>>(count);
+  void* db = dc.io.take<ApiJacobian<F>>(count);
+  ApiJacobian<F>* dout = dc.io.take<ApiJacobian<F>>(count);
+  CU_TRY(ctx, cudaMemcpyAsync(da, a, ja, cudaMemcpyHostToDevice, dc.stream));
+  if (bb) CU_TRY(ctx, cudaMemcpyAsync(db, b, bb, cudaMemcpyHostToDevice, dc.stream));
+  k_test_ec<F><<<(uint32_t)((count + 63) / 64), 64, 0, dc.stream>>>(op, da, db, dout, (uint32_t)count);
+  dc.launches += 1;
+  CU_TRY(ctx, cudaMemcpyAsync(out, dout, ja, cudaMemcpyDeviceToHost, dc.stream));
+  CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  return MSM_OK;
+}
+
+template <class F>
+int to_affine_impl(msm_ctx* ctx, const void* jac, size_t count, int mont_out, void* out_xy, uint8_t* out_inf) {
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const size_t jb = count * sizeof(ApiJacobian<F>), ab = count * sizeof(ApiAffine<F>);
+  CU_TRY(ctx, dc.io.ensure(Arena::padded(jb) + Arena::padded(ab) + Arena::padded(count)));
+  ApiJacobian<F>* dj = dc.io.take<ApiJacobian<F>>(count);
+  ApiAffine<F>* da = dc.io.take<ApiAffine<F>>(count);
+  uint8_t* di = dc.io.take<uint8_t>(count);
+  CU_TRY(ctx, cudaMemcpyAsync(dj, jac, jb, cudaMemcpyHostToDevice, dc.stream));
+  k_to_affine<F><<<(uint32_t)((count + 63) / 64), 64, 0, dc.stream>>>(dj, (uint32_t)count, mont_out, da, di);
+  dc.launches += 1;
+  CU_TRY(ctx, cudaMemcpyAsync(out_xy, da, ab, cudaMemcpyDeviceToHost, dc.stream));
+  if (out_inf) CU_TRY(ctx, cudaMemcpyAsync(out_inf, di, count, cudaMemcpyDeviceToHost, dc.stream));
+  CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  return MSM_OK;
+}
+
+template <class F> int sum_points_impl(msm_ctx* ctx, const void* d_in, size_t count, void* d_out) {
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  k_sum_points<F><<<1, 32, 0, dc.stream>>>(static_cast<const ApiJacobian<F>*>(d_in), (uint32_t)count,
+                                          static_cast<ApiJacobian<F>*>(d_out));
+  dc.launches += 1;
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  return MSM_OK;
+}
+
+template <class F> FieldOps make_field_ops(const char* name) {
+  FieldOps o;
+  o.name = name;
+  o.api_point_bytes = sizeof(ApiAffine<F>);
+  o.packed_point_bytes = sizeof(PackedAffine<F>);
+  o.multiple_multiexp = &multiple_multiexp_impl<F>;
+  o.multiexp = &multiexp_impl<F>;
+  o.convert_bases = &convert_bases_impl<F>;
+  o.synth_points = &synth_points_impl<F>;
+  o.test_fq = &test_fq_impl<F>;
+  o.test_ec = &test_ec_impl<F>;
+  o.to_affine = &to_affine_impl<F>;
+  o.sum_points = &sum_points_impl<F>;
+  return o;
+}
+
+}  // namespace msm

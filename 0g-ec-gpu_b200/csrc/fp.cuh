@@ -240,3 +240,54 @@ template <class P> MSM_COLD Fp<P> fp_inv(const Fp<P>& a) {
 }
 
 }  // namespace msm
+
+// ---------------------------------------------------------------------------------------------
+// FieldSat<P>: the saturated 32-bit-limb field above behind the static interface the curve and
+// MSM templates use (see fp29.cuh for the lazily reduced 29-bit alternative).  Values are always
+// canonical here, so the lazy-reduction hooks (K multiples of p, norm) are no-ops.
+// ---------------------------------------------------------------------------------------------
+namespace msm {
+
+template <class P> struct FieldSat {
+  static constexpr int N = P::N;
+  static constexpr int API_WORDS = P::N;     // words per element at the API boundary
+  static constexpr int PACKED_WORDS = P::N;  // words per resident-base coordinate
+  using Elem = Fp<P>;
+
+  static MSM_HD Elem zero() { return fp_zero<P>(); }
+  static MSM_HD Elem one() { return fp_one<P>(); }
+  static MSM_HD bool is_zero_limbs(const Elem& a) { return fp_is_zero<P>(a); }
+  static MSM_HD Elem add(const Elem& a, const Elem& b) { return fp_add<P>(a, b); }
+  template <int K, int LM> static MSM_HD Elem sub(const Elem& a, const Elem& b) { return fp_sub<P>(a, b); }
+  template <int K, int LM> static MSM_HD Elem neg(const Elem& a) { return fp_neg<P>(a); }
+  static MSM_HD Elem norm(const Elem& a) { return a; }
+  template <int LO, int HI> static MSM_HD bool is_multiple_of_p(const Elem& a) { return fp_is_zero<P>(a); }
+  static MSM_HD Elem mul(const Elem& a, const Elem& b) { return fp_mul<P>(a, b); }
+  static MSM_HD Elem sqr(const Elem& a) { return fp_sqr<P>(a); }
+  static MSM_HD Elem inv(const Elem& a) { return fp_inv<P>(a); }
+
+  // resident-base coordinate <-> registers (same layout as the API: nothing to do)
+  static MSM_HD Elem unpack(const uint32_t* w) {
+    Elem r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = w[i];
+    return r;
+  }
+  static MSM_HD void api_to_packed(const uint32_t* api, uint32_t* packed) {
+#pragma unroll
+    for (int i = 0; i < N; i++) packed[i] = api[i];
+  }
+  static MSM_HD Elem from_api(const uint32_t* w) { return unpack(w); }
+  static MSM_HD void to_api(const Elem& a, uint32_t* w) {
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i] = a.v[i];
+  }
+  // canonical integer (non-Montgomery) in API word layout
+  static MSM_HD void to_canonical_words(const Elem& a, uint32_t* w) {
+    Elem c = fp_from_mont<P>(a);
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i] = c.v[i];
+  }
+};
+
+}  // namespace msm

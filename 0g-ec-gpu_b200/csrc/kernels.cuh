@@ -136,7 +136,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
   return warp_off + x - v;
 }
 
-__global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+static __global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
                              uint32_t* __restrict__ tile_sums) {
   const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS], s = 0;
@@ -155,7 +155,7 @@ __global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t n, uint32
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 // single block: exclusive scan of tile sums in place, total written to *grand_total
-__global__ void k_scan_tile_sums(uint32_t* tile_sums, uint32_t n_tiles, uint32_t* grand_total) {
+static __global__ void k_scan_tile_sums(uint32_t* tile_sums, uint32_t n_tiles, uint32_t* grand_total) {
   uint32_t carry = 0;
   for (uint32_t base = 0; base < n_tiles; base += SCAN_BLOCK) {
     uint32_t i = base + threadIdx.x;
@@ -168,7 +168,7 @@ __global__ void k_scan_tile_sums(uint32_t* tile_sums, uint32_t n_tiles, uint32_t
   if (threadIdx.x == 0) *grand_total = carry;
 }
 // out[i] += tile_offset; also writes the closing element out[n] = grand_total and a copy (cursor)
-__global__ void k_scan_finish(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_sums,
+static __global__ void k_scan_finish(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_sums,
                               const uint32_t* __restrict__ grand_total, uint32_t* __restrict__ cursor) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -181,21 +181,10 @@ __global__ void k_scan_finish(uint32_t* __restrict__ out, uint32_t n, const uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// Point loads: 128-bit loads, read-only path.
+// 128-bit vector loads / stores of plain structs (sizeof multiple of 16, 16-byte aligned).
 // ---------------------------------------------------------------------------------------------
-template <class P> MSM_D Affine<P> load_affine(const Affine<P>* p) {
-  Affine<P> r;
-  constexpr int V = (2 * P::N) / 4;
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-  for (int j = 0; j < V; j++) {
-    uint4 t = __ldg(q + j);
-    o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
-  }
-  return r;
-}
 template <class T> MSM_D void store_vec(T* dst, const T& v) {
+  static_assert(sizeof(T) % 16 == 0, "vector store needs a multiple of 16 bytes");
   constexpr int V = sizeof(T) / 16;
   uint4* q = reinterpret_cast<uint4*>(dst);
   const uint32_t* o = reinterpret_cast<const uint32_t*>(&v);
@@ -203,6 +192,7 @@ template <class T> MSM_D void store_vec(T* dst, const T& v) {
   for (int j = 0; j < V; j++) q[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
 }
 template <class T> MSM_D T load_vec(const T* src) {
+  static_assert(sizeof(T) % 16 == 0, "vector load needs a multiple of 16 bytes");
   T r;
   constexpr int V = sizeof(T) / 16;
   const uint4* q = reinterpret_cast<const uint4*>(src);
@@ -213,6 +203,24 @@ template <class T> MSM_D T load_vec(const T* src) {
     o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
   }
   return r;
+}
+// resident base point: 128-bit loads on the read-only path, then re-slice into field limbs.
+// Returns false for the identity encoding (all words zero).
+template <class F> MSM_D bool load_base(const PackedAffine<F>* p, Affine<F>& out) {
+  constexpr int WORDS = 2 * F::PACKED_WORDS;
+  static_assert(WORDS % 4 == 0, "packed point must be a multiple of 16 bytes");
+  uint32_t w[WORDS];
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint32_t any = 0;
+#pragma unroll
+  for (int j = 0; j < WORDS / 4; j++) {
+    uint4 t = __ldg(q + j);
+    w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+    any |= t.x | t.y | t.z | t.w;
+  }
+  out.x = F::unpack(w);
+  out.y = F::unpack(w + F::PACKED_WORDS);
+  return any != 0;
 }
 
 // largest g in [0, NB) with bucket_start[g] <= pos  (pos < bucket_start[NB])
@@ -229,12 +237,12 @@ MSM_D uint32_t find_bucket(const uint32_t* __restrict__ bucket_start, uint32_t N
 // ---------------------------------------------------------------------------------------------
 // Bucket accumulation.  Thread t of line `blockIdx.y` owns sorted entries [t*S, (t+1)*S).
 // ---------------------------------------------------------------------------------------------
-template <class P>
+template <class F>
 __global__ void __launch_bounds__(128)
-k_accumulate(const Affine<P>* __restrict__ bases, uint32_t line_stride,
+k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
              const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start,
              uint32_t NB, const uint32_t* __restrict__ E_ptr, uint32_t S, uint32_t n_slices,
-             Xyzz<P>* __restrict__ bucket_acc, Xyzz<P>* __restrict__ partials) {
+             Xyzz<F>* __restrict__ bucket_acc, Xyzz<F>* __restrict__ partials) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t E = __ldg(E_ptr);  // = bucket_start[NB], number of non-zero digits
   if (t >= n_slices || (uint64_t)t * S >= E) return;
@@ -248,13 +256,13 @@ k_accumulate(const Affine<P>* __restrict__ bases, uint32_t line_stride,
   uint32_t g = find_bucket(bucket_start, NB, s);
   uint32_t gend = __ldg(bucket_start + g + 1);
   bool started_before = __ldg(bucket_start + g) < s;
-  Xyzz<P> acc = xyzz_inf<P>();
+  Xyzz<F> acc = xyzz_inf<F>();
 
   for (uint32_t pos = s; pos < e; pos++) {
     if (pos == gend) {
       // bucket g is complete: flush and move to the next non-empty bucket
       store_vec(started_before ? &partials[2 * t] : &bucket_acc[g], acc);
-      acc = xyzz_inf<P>();
+      acc = xyzz_inf<F>();
       started_before = false;
       do {
         g++;
@@ -262,10 +270,10 @@ k_accumulate(const Affine<P>* __restrict__ bases, uint32_t line_stride,
       } while (gend == pos);
     }
     const uint32_t ent = __ldg(entries + pos);
-    Affine<P> pt = load_affine<P>(bases + (ent & 0x7fffffffu));
-    if (!aff_is_identity<P>(pt)) {
-      pt = aff_cneg<P>(pt, (ent >> 31) != 0);
-      xyzz_madd<P>(acc, pt);
+    Affine<F> pt;
+    if (load_base<F>(bases + (ent & 0x7fffffffu), pt)) {
+      pt = aff_cneg<F>(pt, (ent >> 31) != 0);
+      xyzz_madd<F>(acc, pt);
     }
   }
   if (gend == e) {
@@ -276,10 +284,10 @@ k_accumulate(const Affine<P>* __restrict__ bases, uint32_t line_stride,
 }
 
 // One thread per bucket: empty -> infinity; cut by slice boundaries -> sum of its partial slots.
-template <class P>
+template <class F>
 __global__ void __launch_bounds__(128)
 k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
-        Xyzz<P>* __restrict__ bucket_acc, const Xyzz<P>* __restrict__ partials) {
+        Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= NB) return;
   const uint32_t line = blockIdx.y;
@@ -287,13 +295,13 @@ k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint
   partials += (size_t)line * 2 * n_slices;
   const uint32_t start = bucket_start[g], end = bucket_start[g + 1];
   if (start == end) {
-    store_vec(&bucket_acc[g], xyzz_inf<P>());
+    store_vec(&bucket_acc[g], xyzz_inf<F>());
     return;
   }
   const uint32_t t0 = start / S, t1 = (end - 1) / S;
   if (t0 == t1) return;  // written directly by k_accumulate
-  Xyzz<P> acc = load_vec(&partials[2 * t0 + 1]);
-  for (uint32_t t = t0 + 1; t <= t1; t++) acc = xyzz_add<P>(acc, load_vec(&partials[2 * t]));
+  Xyzz<F> acc = load_vec(&partials[2 * t0 + 1]);
+  for (uint32_t t = t0 + 1; t <= t1; t++) acc = xyzz_add<F>(acc, load_vec(&partials[2 * t]));
   store_vec(&bucket_acc[g], acc);
 }
 
@@ -302,30 +310,30 @@ k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint
 // Thread j owns Q consecutive buckets: local running sum, plus (first_weight-1) * (plain sum);
 // then a segmented shared-memory tree over RW threads.  Output: one partial per RW threads.
 // ---------------------------------------------------------------------------------------------
-template <class P>
+template <class F>
 __global__ void __launch_bounds__(128)
-k_bucket_reduce(const Xyzz<P>* __restrict__ bucket_acc, uint32_t n_threads, uint32_t B, uint32_t Q,
-                uint32_t RW, Xyzz<P>* __restrict__ out) {
+k_bucket_reduce(const Xyzz<F>* __restrict__ bucket_acc, uint32_t n_threads, uint32_t B, uint32_t Q,
+                uint32_t RW, Xyzz<F>* __restrict__ out) {
   extern __shared__ uint4 smem_raw[];
-  Xyzz<P>* sh = reinterpret_cast<Xyzz<P>*>(smem_raw);
+  Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  Xyzz<P> res = xyzz_inf<P>();
+  Xyzz<F> res = xyzz_inf<F>();
   if (tid < n_threads) {
     const size_t f = (size_t)tid * Q;
     const uint32_t b0 = (uint32_t)(f % B);  // weight of bucket f+k is b0 + k + 1
-    Xyzz<P> run = xyzz_inf<P>();
+    Xyzz<F> run = xyzz_inf<F>();
     for (int k = (int)Q - 1; k >= 0; k--) {
-      run = xyzz_add<P>(run, load_vec(&bucket_acc[f + k]));
-      res = xyzz_add<P>(res, run);
+      run = xyzz_add<F>(run, load_vec(&bucket_acc[f + k]));
+      res = xyzz_add<F>(res, run);
     }
-    if (b0) res = xyzz_add<P>(res, xyzz_mul_small<P>(run, b0));
+    if (b0) res = xyzz_add<F>(res, xyzz_mul_small<F>(run, b0));
   }
   sh[threadIdx.x] = res;
   __syncthreads();
   const uint32_t lane = threadIdx.x & (RW - 1);
   for (uint32_t stride = RW >> 1; stride >= 1; stride >>= 1) {
     if (lane < stride) {
-      res = xyzz_add<P>(res, sh[threadIdx.x + stride]);
+      res = xyzz_add<F>(res, sh[threadIdx.x + stride]);
       sh[threadIdx.x] = res;
     }
     __syncthreads();
@@ -334,94 +342,112 @@ k_bucket_reduce(const Xyzz<P>* __restrict__ bucket_acc, uint32_t n_threads, uint
 }
 
 // One block per task (line, chunk): thread w sums the PG partials of window w; thread 0 folds the
-// windows Horner-style (c doublings per step) and writes the Jacobian result.
-template <class P>
-__global__ void k_window_combine(const Xyzz<P>* __restrict__ group_partials, uint32_t W, uint32_t PG,
-                                 uint32_t c, Jacobian<P>* __restrict__ out) {
+// windows Horner-style (c doublings per step) and writes the Jacobian result in the API layout.
+template <class F>
+__global__ void k_window_combine(const Xyzz<F>* __restrict__ group_partials, uint32_t W, uint32_t PG,
+                                 uint32_t c, ApiJacobian<F>* __restrict__ out) {
   extern __shared__ uint4 smem_raw[];
-  Xyzz<P>* sh = reinterpret_cast<Xyzz<P>*>(smem_raw);
+  Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw);
   const uint32_t task = blockIdx.x;
   for (uint32_t w = threadIdx.x; w < W; w += blockDim.x) {
-    const Xyzz<P>* src = group_partials + ((size_t)task * W + w) * PG;
-    Xyzz<P> s = load_vec(src);
-    for (uint32_t k = 1; k < PG; k++) s = xyzz_add<P>(s, load_vec(src + k));
+    const Xyzz<F>* src = group_partials + ((size_t)task * W + w) * PG;
+    Xyzz<F> s = load_vec(src);
+    for (uint32_t k = 1; k < PG; k++) s = xyzz_add<F>(s, load_vec(src + k));
     sh[w] = s;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    Xyzz<P> acc = sh[W - 1];
+    Xyzz<F> acc = sh[W - 1];
     for (int w = (int)W - 2; w >= 0; w--) {
-      for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl<P>(acc);
-      acc = xyzz_add<P>(acc, sh[w]);
+      for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl<F>(acc);
+      acc = xyzz_add<F>(acc, sh[w]);
     }
-    out[task] = xyzz_to_jacobian<P>(acc);
+    xyzz_to_api_jacobian<F>(acc, &out[task]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Small helpers: sum of Jacobian points, Jacobian -> affine, per-primitive test kernels
-// (counterpart of ag-build/cl/test.cl), synthetic inputs.
+// Boundary and helper kernels: resident-copy conversion, sum of Jacobian points, Jacobian ->
+// affine, per-primitive test kernels (counterpart of ag-build/cl/test.cl), synthetic inputs.
 // ---------------------------------------------------------------------------------------------
-template <class P>
-__global__ void k_sum_points(const Jacobian<P>* __restrict__ in, uint32_t count, Jacobian<P>* __restrict__ out) {
+template <class F>
+__global__ void k_convert_bases(const ApiAffine<F>* __restrict__ in, uint32_t n, PackedAffine<F>* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ApiAffine<F> a = in[i];
+  PackedAffine<F> o;
+  F::api_to_packed(a.x, o.x);  // identity (0,0) stays all-zero
+  F::api_to_packed(a.y, o.y);
+  out[i] = o;
+}
+
+template <class F>
+__global__ void k_sum_points(const ApiJacobian<F>* __restrict__ in, uint32_t count, ApiJacobian<F>* __restrict__ out) {
   if (blockIdx.x || threadIdx.x) return;
-  Xyzz<P> acc = xyzz_inf<P>();
-  for (uint32_t i = 0; i < count; i++) acc = xyzz_add<P>(acc, xyzz_from_jacobian<P>(in[i]));
-  out[0] = xyzz_to_jacobian<P>(acc);
+  Xyzz<F> acc = xyzz_inf<F>();
+  for (uint32_t i = 0; i < count; i++) acc = xyzz_add<F>(acc, xyzz_from_api_jacobian<F>(&in[i]));
+  xyzz_to_api_jacobian<F>(acc, &out[0]);
 }
 
-template <class P>
-__global__ void k_to_affine(const Jacobian<P>* __restrict__ in, uint32_t count, int mont_out,
-                            Affine<P>* __restrict__ out, uint8_t* __restrict__ is_inf) {
+template <class F>
+__global__ void k_to_affine(const ApiJacobian<F>* __restrict__ in, uint32_t count, int mont_out,
+                            ApiAffine<F>* __restrict__ out, uint8_t* __restrict__ is_inf) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  Xyzz<P> x = xyzz_from_jacobian<P>(in[i]);
-  Affine<P> a = xyzz_to_affine<P>(x);
-  const bool inf = xyzz_is_inf<P>(x);
-  if (!inf && !mont_out) {
-    a.x = fp_from_mont<P>(a.x);
-    a.y = fp_from_mont<P>(a.y);
-  }
-  out[i] = a;
-  is_inf[i] = inf ? 1 : 0;
+  Xyzz<F> x = xyzz_from_api_jacobian<F>(&in[i]);
+  is_inf[i] = xyzz_to_api_affine<F>(x, mont_out != 0, &out[i]) ? 1 : 0;
 }
 
-template <class P>
-__global__ void k_test_fq(int op, const Fp<P>* __restrict__ a, const Fp<P>* __restrict__ b,
-                          Fp<P>* __restrict__ o, uint32_t count) {
+template <class F> struct ApiElem {
+  uint32_t w[F::API_WORDS];
+};
+
+// r2 / unit: API words of R^2 mod p and of the integer 1 (for the mont / unmont test ops)
+template <class F>
+__global__ void k_test_fq(int op, const ApiElem<F>* __restrict__ a, const ApiElem<F>* __restrict__ b,
+                          ApiElem<F> r2, ApiElem<F>* __restrict__ o, uint32_t count) {
+  using E = typename F::Elem;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  Fp<P> x = a[i], y = b ? b[i] : fp_zero<P>(), r;
+  ApiElem<F> wa = a[i], wb = wa, wo;
+  if (b) wb = b[i];
+  E x = F::norm(F::from_api(wa.w)), y = F::norm(F::from_api(wb.w)), r;
   switch (op) {
-    case 0: r = fp_add<P>(x, y); break;
-    case 1: r = fp_sub<P>(x, y); break;
-    case 2: r = fp_mul<P>(x, y); break;
-    case 3: r = fp_sqr<P>(x); break;
-    case 4: r = fp_dbl<P>(x); break;
-    case 5: r = fp_to_mont<P>(x); break;
-    case 6: r = fp_from_mont<P>(x); break;
-    case 7: r = fp_inv<P>(x); break;
-    default: r = fp_neg<P>(x); break;
+    case 0: r = F::add(x, y); break;
+    case 1: r = F::template sub<2, 1>(x, y); break;
+    case 2: r = F::mul(x, y); break;
+    case 3: r = F::sqr(x); break;
+    case 4: r = F::add(x, x); break;
+    case 5: r = F::mul(x, F::from_api(r2.w)); break;                 // to Montgomery form
+    case 6: {                                                         // from Montgomery form
+      ApiElem<F> unit;
+      for (int k = 0; k < F::API_WORDS; k++) unit.w[k] = k == 0 ? 1u : 0u;
+      r = F::mul(x, F::from_api(unit.w));
+      break;
+    }
+    case 7: r = F::inv(x); break;
+    default: r = F::template neg<2, 1>(x); break;
   }
-  o[i] = r;
+  F::to_api(r, wo.w);
+  o[i] = wo;
 }
 
-template <class P>
-__global__ void k_test_ec(int op, const Jacobian<P>* __restrict__ a, const void* __restrict__ b,
-                          Jacobian<P>* __restrict__ o, uint32_t count) {
+template <class F>
+__global__ void k_test_ec(int op, const ApiJacobian<F>* __restrict__ a, const void* __restrict__ b,
+                          ApiJacobian<F>* __restrict__ o, uint32_t count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  Xyzz<P> x = xyzz_from_jacobian<P>(a[i]), r;
+  Xyzz<F> x = xyzz_from_api_jacobian<F>(&a[i]), r;
   if (op == 0) {
-    r = xyzz_add<P>(x, xyzz_from_jacobian<P>(reinterpret_cast<const Jacobian<P>*>(b)[i]));
+    r = xyzz_add<F>(x, xyzz_from_api_jacobian<F>(reinterpret_cast<const ApiJacobian<F>*>(b) + i));
   } else if (op == 1) {
-    Affine<P> q = reinterpret_cast<const Affine<P>*>(b)[i];
+    Affine<F> q = affine_from_api<F>(reinterpret_cast<const ApiAffine<F>*>(b) + i);
     r = x;
-    if (!aff_is_identity<P>(q)) xyzz_madd<P>(r, q);
+    if (!aff_is_identity<F>(q)) xyzz_madd<F>(r, q);
   } else {
-    r = xyzz_dbl<P>(x);
+    r = xyzz_dbl<F>(x);
   }
-  o[i] = xyzz_to_jacobian<P>(r);
+  xyzz_to_api_jacobian<F>(r, &o[i]);
 }
 
 // --- synthetic inputs -------------------------------------------------------------------------
@@ -437,7 +463,7 @@ struct ScalarField {
   uint32_t bits;
 };
 
-__global__ void k_synth_scalars(ScalarField fr, uint64_t seed, uint64_t start, uint32_t n,
+static __global__ void k_synth_scalars(ScalarField fr, uint64_t seed, uint64_t start, uint32_t n,
                                 uint32_t* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -467,16 +493,18 @@ __global__ void k_synth_scalars(ScalarField fr, uint64_t seed, uint64_t start, u
 
 // P_i = (a + (start+i) b) G.  Each thread produces RUN consecutive points: one double-and-add for
 // its first point, RUN-1 mixed additions of D = b*G, then one shared inversion (Montgomery's
-// trick) to normalise them.  gen / d are affine Montgomery.
+// trick) to normalise them.  gen / d are affine in the API layout; so is the output.
 constexpr int SYNTH_RUN = 16;
-template <class P>
+template <class F>
 __global__ void __launch_bounds__(64)
-k_synth_points(Affine<P> gen, Affine<P> d, uint64_t a, uint64_t b, uint64_t start, uint32_t n,
-               Affine<P>* __restrict__ out) {
+k_synth_points(ApiAffine<F> gen_api, ApiAffine<F> d_api, uint64_t a, uint64_t b, uint64_t start, uint32_t n,
+               ApiAffine<F>* __restrict__ out) {
+  using E = typename F::Elem;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t i0 = (uint64_t)t * SYNTH_RUN;
   if (i0 >= n) return;
   const uint32_t cnt = (uint32_t)min((uint64_t)SYNTH_RUN, (uint64_t)n - i0);
+  const Affine<F> gen = affine_from_api<F>(&gen_api), d = affine_from_api<F>(&d_api);
   // k = a + (start + i0) * b, up to 129 bits
   const uint64_t m = start + i0;
   const uint64_t lo = m * b, hi = __umul64hi(m, b);
@@ -484,29 +512,29 @@ k_synth_points(Affine<P> gen, Affine<P> d, uint64_t a, uint64_t b, uint64_t star
   uint64_t c0 = k0 < lo ? 1 : 0;
   uint64_t k1 = hi + c0;
   uint64_t k2 = k1 < hi ? 1 : 0;
-  Xyzz<P> acc = xyzz_inf<P>();
+  Xyzz<F> acc = xyzz_inf<F>();
   for (int bit = 128; bit >= 0; bit--) {
-    acc = xyzz_dbl<P>(acc);
+    acc = xyzz_dbl<F>(acc);
     const uint64_t word = bit >= 128 ? k2 : (bit >= 64 ? k1 : k0);
-    if ((word >> (bit & 63)) & 1) xyzz_madd<P>(acc, gen);
+    if ((word >> (bit & 63)) & 1) xyzz_madd<F>(acc, gen);
   }
-  Xyzz<P> pts[SYNTH_RUN];
-  Fp<P> pref[SYNTH_RUN];
-  Fp<P> prod = fp_one<P>();
+  Xyzz<F> pts[SYNTH_RUN];
+  E pref[SYNTH_RUN];
+  E prod = F::one();
   for (uint32_t j = 0; j < cnt; j++) {
     pts[j] = acc;
     pref[j] = prod;
-    prod = fp_mul<P>(prod, fp_mul<P>(acc.zz, acc.zzz));  // never infinity: k < group order
-    xyzz_madd<P>(acc, d);
+    prod = F::mul(prod, F::mul(acc.zz, acc.zzz));  // never infinity: k < group order
+    xyzz_madd<F>(acc, d);
   }
-  Fp<P> inv = fp_inv<P>(prod);
+  E inv = F::inv(prod);
   for (int j = (int)cnt - 1; j >= 0; j--) {
-    Fp<P> zi = fp_mul<P>(inv, pref[j]);  // 1 / (zz*zzz)
-    inv = fp_mul<P>(inv, fp_mul<P>(pts[j].zz, pts[j].zzz));
-    Affine<P> o;
-    o.x = fp_mul<P>(pts[j].x, fp_mul<P>(zi, pts[j].zzz));
-    o.y = fp_mul<P>(pts[j].y, fp_mul<P>(zi, pts[j].zz));
-    store_vec(&out[i0 + j], o);
+    const E zi = F::mul(inv, pref[j]);  // 1 / (zz*zzz)
+    inv = F::mul(inv, F::mul(pts[j].zz, pts[j].zzz));
+    ApiAffine<F> o;
+    F::to_api(F::mul(pts[j].x, F::mul(zi, pts[j].zzz)), o.x);
+    F::to_api(F::mul(pts[j].y, F::mul(zi, pts[j].zz)), o.y);
+    out[i0 + j] = o;
   }
 }
 

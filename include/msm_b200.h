@@ -86,6 +86,12 @@ const char* msm_last_error(const msm_ctx* ctx);
 int msm_last_timings(const msm_ctx* ctx, msm_timings* out);
 /* Window-size override for experiments (0 = automatic).  Results never depend on it. */
 int msm_set_window_bits(msm_ctx* ctx, uint32_t c);
+/* Name of the field implementation behind this context ("bn254/u29", "bn254/sat32", "bls12-381/sat32"). */
+const char* msm_field_impl(const msm_ctx* ctx);
+/* Run device 0's work on a caller-owned cudaStream_t (e.g. the framework's current stream), so that
+ * the caller's own stream-ordered work and events see it; NULL restores a private stream.  The
+ * reference creates a fresh NON_BLOCKING stream per kernel (ag-cuda-proxy/src/module.rs:56-62). */
+int msm_set_stream(msm_ctx* ctx, void* cuda_stream);
 
 /* ---- resident bases -------------------------------------------------------------------- */
 /* upload_multiexp_bases (ag-cuda-ec/src/multiexp.rs:12-19): copy n_points {x,y} Montgomery
@@ -94,8 +100,9 @@ int msm_bases_upload(msm_ctx* ctx, const void* xy_mont, size_t n_points, msm_bas
 /* Same, but split contiguously over all devices of the context, ceil(n/devices) points each:
  * the partition MultiexpKernel::parallel_multiexp uses (ec-gpu-proxy/src/multiexp.rs:329-337). */
 int msm_bases_upload_sharded(msm_ctx* ctx, const void* xy_mont, size_t n_points, msm_bases** out);
-/* Wrap points that already live in device memory of device 0 (no copy, not owned). */
-int msm_bases_wrap_device(msm_ctx* ctx, const void* d_xy_mont, size_t n_points, msm_bases** out);
+/* Same as msm_bases_upload with the source points already in device memory of device 0 (same
+ * {x,y} Montgomery layout); the engine keeps its own resident copy, the source may be freed. */
+int msm_bases_from_device(msm_ctx* ctx, const void* d_xy_mont, size_t n_points, msm_bases** out);
 /* DeviceData::size (ag-cuda-proxy/src/params.rs:209): bytes. */
 size_t msm_bases_size_bytes(const msm_bases* b);
 size_t msm_bases_num_points(const msm_bases* b);
@@ -117,6 +124,13 @@ int msm_multiple_multiexp(msm_ctx* ctx, const msm_bases* bases, const void* scal
  * used for device-resident timing).  Returns after the result is complete. */
 int msm_multiple_multiexp_device(msm_ctx* ctx, const msm_bases* bases, const void* d_scalars,
                                  size_t L, uint32_t num_chunks, void* d_out_jacobian);
+
+/* The same call repeated `repeats` times back to back with CUDA events recorded on the launching
+ * stream around the whole sequence (total_ms) and around every bucket-accumulation kernel (their
+ * sum in accumulate_ms).  Measurement aid for bench.py; results as above. */
+int msm_multiple_multiexp_device_timed(msm_ctx* ctx, const msm_bases* bases, const void* d_scalars,
+                                       size_t L, uint32_t num_chunks, void* d_out_jacobian,
+                                       uint32_t repeats, float* total_ms, float* accumulate_ms);
 
 /* MultiexpKernel::multiexp (ec-gpu-proxy/src/multiexp.rs:372-400): one MSM over n host points
  * and n host scalars (the Rust shim applies `skip` as a pointer offset), split over all devices

@@ -1,0 +1,144 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures of tests/golden/.
+
+  pyref_vectors.json   from oracle/pyref.py (independent pure-Python big-integer arithmetic):
+                       field products, curve KATs, small MSMs incl. edge cases -- needs nothing
+                       but Python.
+  ref_cl_vectors.json  from oracle/_ref (the REFERENCE'S OWN device sources ag-build/cl/*.cl,
+                       compiled for the host by oracle/build_ref.py and run in this container):
+                       FIELD_add/sub/mul/sqr/double/mont/unmont, POINT_add/add_mixed/double and the
+                       POINT_multiexp kernel.  Needs /root/reference; the fixture travels instead.
+
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyref as P  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SEED = 0x0BADC0DE
+
+
+def hx(b):
+    return bytes(b).hex()
+
+
+def make_pyref():
+    out = {"generator": "tests/golden/make_golden.py (oracle/pyref.py)", "curves": {}}
+    for cv in (P.BN254, P.BLS12_381):
+        rng = np.random.default_rng(2024 + cv.curve_id)
+        c = {}
+        # field products in the API Montgomery domain: mont(a)*mont(b)/R = mont(a*b)
+        fa = [int.from_bytes(rng.bytes(cv.fq_bytes + 8), "little") % cv.p for _ in range(16)]
+        fb = [int.from_bytes(rng.bytes(cv.fq_bytes + 8), "little") % cv.p for _ in range(16)]
+        fa[:3], fb[:3] = [0, 1, cv.p - 1], [cv.p - 1, cv.p - 1, cv.p - 1]
+        c["fq_mul"] = {
+            "a_mont": [hx(cv.fq_to_bytes(cv.to_mont(x))) for x in fa],
+            "b_mont": [hx(cv.fq_to_bytes(cv.to_mont(x))) for x in fb],
+            "ab_mont": [hx(cv.fq_to_bytes(cv.to_mont(x * y % cv.p))) for x, y in zip(fa, fb)],
+            "a_plus_b_mont": [hx(cv.fq_to_bytes(cv.to_mont((x + y) % cv.p))) for x, y in zip(fa, fb)],
+            "a_minus_b_mont": [hx(cv.fq_to_bytes(cv.to_mont((x - y) % cv.p))) for x, y in zip(fa, fb)],
+        }
+        # multiples of the generator (canonical affine)
+        c["kG"] = {str(k): [hex(v) for v in cv.mul(k, cv.g)] for k in (1, 2, 3, 7, cv.r - 1)}
+        # synthetic-input generator prefix
+        n = 40
+        sc = P.gen_scalars(cv, SEED, 0, n)
+        pts = P.gen_points(cv, SEED, 0, n)
+        c["synthetic"] = {"seed": SEED, "scalars": hx(P.scalars_to_bytes(sc)), "points_mont": hx(P.points_to_bytes(cv, pts))}
+        # MSMs: plain, and with edge cases
+        cases = []
+        cases.append(("random40", sc, pts))
+        esc, epts = list(sc), list(pts)
+        esc[0], esc[1], esc[2] = 0, 1, cv.r - 1
+        epts[3] = None                      # identity base
+        epts[5], esc[5] = epts[4], esc[4]   # repeated (point, scalar)
+        epts[7], esc[7] = cv.neg(epts[6]), esc[6]  # P and -P with equal scalars
+        esc[8] = (1 << 128) - 1
+        esc[9] = 0x8000
+        esc[10] = 0xFFFF
+        cases.append(("edge40", esc, epts))
+        cases.append(("single", [sc[0]], [pts[0]]))
+        cases.append(("all_zero_scalars", [0] * 8, pts[:8]))
+        c["msm"] = []
+        for name, s, p in cases:
+            res = cv.msm(s, p)
+            c["msm"].append({
+                "name": name,
+                "scalars": hx(P.scalars_to_bytes(s)),
+                "points_mont": hx(P.points_to_bytes(cv, p)),
+                "result_affine": None if res is None else [hex(res[0]), hex(res[1])],
+            })
+        # batched shape: 2 lines x 4 chunks x 8 points (ag_cuda_ec::multiple_multiexp semantics)
+        L, lines, chunks = 32, 2, 4
+        bsc = P.gen_scalars(cv, SEED + 1, 0, L)
+        bpts = P.gen_points(cv, SEED + 1, 0, L * lines)
+        res = []
+        cl = L // chunks
+        for line in range(lines):
+            for ch in range(chunks):
+                r = cv.msm(bsc[ch * cl:(ch + 1) * cl], bpts[line * L + ch * cl: line * L + (ch + 1) * cl])
+                res.append(None if r is None else [hex(r[0]), hex(r[1])])
+        c["multiple_multiexp"] = {"L": L, "lines": lines, "chunks": chunks, "scalars": hx(P.scalars_to_bytes(bsc)),
+                                  "points_mont": hx(P.points_to_bytes(cv, bpts)), "results_affine": res}
+        out["curves"][cv.name] = c
+    with open(os.path.join(HERE, "pyref_vectors.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+def make_ref_cl():
+    from oracle import oracle as O
+    from oracle import ref_cl as R
+
+    if not os.path.isdir("/root/reference/ag-build/cl"):
+        print("reference sources absent: ref_cl_vectors.json not regenerated")
+        return
+    out = {"generator": "tests/golden/make_golden.py (oracle/_ref = /root/reference/ag-build/cl/*.cl built for the host)",
+           "curves": {}}
+    for curve, name in ((0, "bn254"), (1, "bls12_381")):
+        fq = O.FQ_BYTES[curve]
+        rng = np.random.default_rng(77 + curve)
+        p = int.from_bytes(O.constant(curve, 0).tobytes(), "little")
+        n = 12
+        vals_a = [int.from_bytes(rng.bytes(fq + 8), "little") % p for _ in range(n)]
+        vals_b = [int.from_bytes(rng.bytes(fq + 8), "little") % p for _ in range(n)]
+        vals_a[:2], vals_b[:2] = [0, p - 1], [p - 1, p - 1]
+        a = np.frombuffer(b"".join(v.to_bytes(fq, "little") for v in vals_a), dtype=np.uint8).copy()
+        b = np.frombuffer(b"".join(v.to_bytes(fq, "little") for v in vals_b), dtype=np.uint8).copy()
+        c = {"fq": {"a": hx(a), "b": hx(b), "ops": {}}}
+        for op, nm in enumerate(["add", "sub", "mul", "sqr", "double", "mont", "unmont"]):
+            c["fq"]["ops"][nm] = hx(R.fq_op(curve, op, a, b))
+        # curve ops on Jacobian inputs produced by the reference's own arithmetic (k*P by repeated ops)
+        pts = O.gen_points(curve, 11, n)
+        one = O.constant(curve, 1)
+        lifted = np.zeros((n, 3 * fq), dtype=np.uint8)
+        lifted[:, :2 * fq] = pts
+        lifted[:, 2 * fq:] = one
+        dbl = R.ec_op(curve, 2, lifted)
+        trip = R.ec_op(curve, 1, dbl, pts)
+        c["ec"] = {"affine": hx(pts), "double": hx(dbl), "double_plus_affine": hx(trip),
+                   "add_double_triple": hx(R.ec_op(curve, 0, dbl, trip))}
+        # POINT_multiexp kernel: 2 lines x 4 chunks x 16 points
+        L, lines, chunks = 64, 2, 4
+        sc = O.gen_scalars(curve, SEED + 2, L)
+        bp = O.gen_points(curve, SEED + 2, L * lines)
+        c["multiexp"] = {"L": L, "lines": lines, "chunks": chunks, "scalars": hx(sc), "points_mont": hx(bp), "runs": []}
+        for w, neg in ((3, True), (4, False), (7, True)):
+            c["multiexp"]["runs"].append({"window_size": w, "neg_is_cheap": neg,
+                                          "results_jacobian": hx(R.multiple_multiexp(curve, bp, sc, chunks, w, neg))})
+        out["curves"][name] = c
+    with open(os.path.join(HERE, "ref_cl_vectors.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    make_pyref()
+    make_ref_cl()
+    for fn in ("pyref_vectors.json", "ref_cl_vectors.json"):
+        print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")

@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Device-resident timing sweep through the C ABI (development aid; bench.py is the contract)."""
+import ctypes
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ec_gpu_b200 as m  # noqa: E402
+
+
+def main():
+    lib = m.load_library()
+    curve = int(os.environ.get("CURVE", "0"))
+    sizes = [int(x) for x in (sys.argv[1:] or ["16", "20", "22", "24"])]
+    windows = [int(x) for x in os.environ.get("WINDOWS", "0").split(",")]
+    ws = m.Workspace(curve)
+    h = ws.handle
+    print("field impl:", lib.msm_field_impl(h).decode())
+    fq = m.fq_bytes(curve)
+    for lg in sizes:
+        n = 1 << lg
+        dp, ds, do = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        assert lib.msm_device_alloc(h, n * 2 * fq, ctypes.byref(dp)) == 0
+        assert lib.msm_device_alloc(h, n * 32, ctypes.byref(ds)) == 0
+        assert lib.msm_device_alloc(h, 3 * fq, ctypes.byref(do)) == 0
+        t0 = time.time()
+        assert lib.msm_synth_points_device(h, 0x0BADC0DE, 0, n, dp) == 0
+        assert lib.msm_synth_scalars_device(h, 0x0BADC0DE, 0, n, ds) == 0
+        t1 = time.time()
+        bh = ctypes.c_void_p()
+        assert lib.msm_bases_from_device(h, dp, n, ctypes.byref(bh)) == 0
+        lib.msm_device_free(h, dp)
+        for c in windows:
+            ws.set_window_bits(c)
+            best = None
+            for it in range(4):
+                rc = lib.msm_multiple_multiexp_device(h, bh, ds, n, 1, do)
+                assert rc == 0, (rc, lib.msm_last_error(h))
+                t = ws.timings()
+                if it > 0 and (best is None or t["total_ms"] < best["total_ms"]):
+                    best = t
+            pts = n / (best["total_ms"] * 1e-3)
+            print(json.dumps({"log_n": lg, "c": best["window_bits"], "W": best["num_windows"],
+                              "total_ms": round(best["total_ms"], 3), "sort_ms": round(best["sort_ms"], 3),
+                              "acc_ms": round(best["accumulate_ms"], 3), "red_ms": round(best["reduce_ms"], 3),
+                              "points_per_s": round(pts), "imad_roofline_frac": round(pts * 21760 / 1.8612e13, 4),
+                              "synth_s": round(t1 - t0, 2)}))
+        ws.set_window_bits(0)
+        lib.msm_bases_free(bh)
+        lib.msm_device_free(h, ds)
+        lib.msm_device_free(h, do)
+
+
+if __name__ == "__main__":
+    main()
