@@ -233,15 +233,24 @@ int msm_bases_upload_sharded(msm_ctx* ctx, const void* xy, size_t n, msm_bases**
 int msm_bases_from_device(msm_ctx* ctx, const void* d_xy, size_t n, msm_bases** out) {
   return make_resident(ctx, d_xy, n, false, true, out);
 }
+int msm_bases_precompute(msm_ctx* ctx, msm_bases* b, uint32_t window_bits) {
+  if (!ctx || !b || b->ctx != ctx) return MSM_ERR_INVALID;
+  LOCK_OR_BUSY(ctx);
+  for (auto& sh : b->shards) {
+    int rc = ctx->ops->build_table(ctx, sh, window_bits);
+    if (rc != MSM_OK) return rc;
+  }
+  return MSM_OK;
+}
+uint32_t msm_bases_table_window(const msm_bases* b) { return (b && !b->shards.empty()) ? b->shards[0].table_c : 0; }
 size_t msm_bases_size_bytes(const msm_bases* b) { return b ? b->n * b->ctx->ops->api_point_bytes : 0; }
 size_t msm_bases_num_points(const msm_bases* b) { return b ? b->n : 0; }
 int msm_bases_free(msm_bases* b) {
   if (!b) return MSM_ERR_INVALID;
   for (auto& s : b->shards) {
-    if (s.owned && s.ptr) {
-      cudaSetDevice(b->ctx->devs[s.dev_idx].dev);
-      cudaFree(s.ptr);
-    }
+    if ((s.owned && s.ptr) || s.table) cudaSetDevice(b->ctx->devs[s.dev_idx].dev);
+    if (s.owned && s.ptr) cudaFree(s.ptr);
+    if (s.table) cudaFree(s.table);
   }
   delete b;
   return MSM_OK;

@@ -85,6 +85,8 @@ struct msm_bases {
     void* ptr;  // resident copy in the field's packed layout
     size_t start, n;
     bool owned;
+    void* table = nullptr;     // optional window table T[w][i] = 2^(c w) P_i (msm_bases_precompute)
+    uint32_t table_c = 0, table_W = 0;
   };
   std::vector<Shard> shards;
 };
@@ -120,6 +122,8 @@ struct FieldOps {
                   size_t n, void* out);
   // d_api (device, API layout) -> d_packed (device, resident layout); enqueued on dc.stream
   int (*convert_bases)(msm_ctx*, DeviceCtx&, const void* d_api, size_t n, void* d_packed);
+  // window table for one shard (allocates sh.table); c == 0: the engine's choice for shard-sized MSMs
+  int (*build_table)(msm_ctx*, msm_bases::Shard& sh, uint32_t c);
   int (*synth_points)(msm_ctx*, uint64_t seed, size_t start, size_t n, void* d_out);
   int (*test_fq)(msm_ctx*, int op, const void* a, const void* b, void* out, size_t count);
   int (*test_ec)(msm_ctx*, int op, const void* a, const void* b, void* out, size_t count);

@@ -40,14 +40,18 @@ inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_task
 struct Plan {
   Geometry geo;
   uint32_t n_lines, S, n_slices, Q, RW, PG, n_tasks;
+  uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
   uint64_t E_max;
   size_t scratch_bytes;
 };
 
+// table_c != 0: the bases are a window table built for window size table_c covering exactly L points
 template <class F>
-int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, Plan& pl) {
+int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, Plan& pl, uint32_t table_c = 0) {
   if (L == 0 || num_chunks == 0 || n_lines == 0 || num_chunks > L) return MSM_ERR_INVALID;
   Geometry& g = pl.geo;
+  g.fold = table_c ? 1 : 0;
+  g.table_stride = L;
   g.num_chunks = num_chunks;
   g.chunk_len = L / num_chunks;  // tail dropped, as ag-build/cl/multiexp.cl:235
   g.L = g.chunk_len * num_chunks;
@@ -57,23 +61,34 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     if (!c) c = (uint32_t)atoi(env);
   }
   if (c < 2 || c > 24) c = choose_window(g.chunk_len, g.scalar_bits, (uint64_t)num_chunks * n_lines, sizeof(Xyzz<F>));
+  if (table_c) c = table_c;
   g.c = c;
   g.W = (g.scalar_bits + 1 + c - 1) / c;
   g.B = 1u << (c - 1);
-  const uint64_t NB = (uint64_t)num_chunks * g.W * g.B;
+  pl.W_sets = g.fold ? 1 : g.W;
+  const uint64_t NB = (uint64_t)num_chunks * pl.W_sets * g.B;
   if (NB >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
   g.NB = (uint32_t)NB;
   pl.n_lines = n_lines;
   pl.n_tasks = n_lines * num_chunks;
   pl.E_max = (uint64_t)g.L * g.W;
-  if (pl.E_max >= (1ull << 32) || (uint64_t)L * n_lines >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
+  if (pl.E_max >= (1ull << 31) || (uint64_t)L * n_lines >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
   // slice length: enough slices to fill the machine several times over, few cut buckets
   uint32_t S = (uint32_t)(pl.E_max / (148ull * 512 * 8));
   if (const char* env = getenv("MSM_B200_SLICE")) S = (uint32_t)atoi(env);
   S = S < 8 ? 8 : (S > 1024 ? 1024 : S);
   pl.S = S;
   pl.n_slices = (uint32_t)((pl.E_max + S - 1) / S);
-  pl.Q = g.B < 8 ? g.B : 8;
+  // buckets per reduction thread: the per-thread fix-up (first_weight * plain sum, a ~c-bit
+  // double-and-add) is amortised over Q buckets; keep about one wave of threads on the machine
+  {
+    const uint64_t total_buckets = (uint64_t)g.NB * n_lines;
+    uint32_t Q = 8;
+    while (Q < 256 && total_buckets / Q > 131072) Q <<= 1;
+    if (const char* env = getenv("MSM_B200_REDUCE_Q")) Q = (uint32_t)atoi(env);
+    while (Q > g.B) Q >>= 1;
+    pl.Q = Q < 1 ? 1 : Q;
+  }
   const uint32_t TG = g.B / pl.Q;
   pl.RW = TG < 128 ? TG : 128;
   pl.PG = TG / pl.RW;
@@ -84,7 +99,8 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   b += Arena::padded(pl.E_max * 4);                                          // entries
   b += Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));              // bucket accumulators
   b += Arena::padded((size_t)2 * pl.n_slices * n_lines * sizeof(Xyzz<F>));   // slice partials
-  b += Arena::padded((size_t)pl.n_tasks * g.W * pl.PG * sizeof(Xyzz<F>));    // group partials
+  b += 2 * Arena::padded((size_t)pl.n_tasks * pl.W_sets * pl.PG * sizeof(Xyzz<F>));  // group partials (ping-pong)
+  b += Arena::padded((size_t)(n_lines + (size_t)n_lines * (pl.n_slices / HEAVY_SPAN + 1)) * 4);  // heavy-bucket work list
   pl.scratch_bytes = b;
   return MSM_OK;
 }
@@ -103,18 +119,37 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
   uint32_t* entries = dc.arena.take<uint32_t>(pl.E_max);
   Xyzz<F>* bucket_acc = dc.arena.take<Xyzz<F>>((size_t)g.NB * pl.n_lines);
   Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * pl.n_slices * pl.n_lines);
-  Xyzz<F>* group_partials = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * g.W * pl.PG);
+  Xyzz<F>* group_partials = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
+  Xyzz<F>* group_partials2 = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
+  const uint32_t heavy_cap = pl.n_slices / HEAVY_SPAN + 1;
+  uint32_t* heavy_count = dc.arena.take<uint32_t>(pl.n_lines + (size_t)pl.n_lines * heavy_cap);
+  uint32_t* heavy_list = heavy_count + pl.n_lines;
   cudaStream_t st = dc.stream;
 
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
   // --- sort: histogram, scan, scatter
   CU_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.NB + 1) * 4, st));
   const uint32_t db = 256, dg = (g.L + db - 1) / db;
-  k_digits<false><<<dg, db, 0, st>>>(d_scalars, g, counts, nullptr);
+  k_digits<false><<<dg, db, 0, st>>>(d_scalars, g, counts, nullptr, 0u, g.NB);
   k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
   k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
   k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(bucket_start, g.NB, tile_sums, tile_sums + n_tiles, cursor);
-  k_digits<true><<<dg, db, 0, st>>>(d_scalars, g, cursor, entries);
+  {
+    // scatter in bucket-range passes: each pass writes a bounded slice of `entries` at random, which
+    // the 126 MB L2 partly absorbs; every pass re-reads the scalars (sequential)
+    // (measured at 2^24: 4 passes best for c = 22 folded, 1-2 for c = 16; every pass repeats the
+    // digit extraction, so more passes stop paying quickly)
+    uint32_t passes = (uint32_t)((pl.E_max * 4 + (200u << 20) - 1) / (200u << 20));
+    if (const char* env = getenv("MSM_B200_SCATTER_PASSES")) passes = (uint32_t)atoi(env);
+    passes = passes < 1 ? 1 : (passes > 8 ? 8 : passes);
+    const uint32_t per = (g.NB + passes - 1) / passes;
+    for (uint32_t ps = 0; ps < passes; ps++) {
+      const uint32_t lo = ps * per, hi = lo + per < g.NB ? lo + per : g.NB;
+      if (lo >= hi) break;
+      k_digits<true><<<dg, db, 0, st>>>(d_scalars, g, cursor, entries, lo, hi);
+      dc.launches += 1;
+    }
+  }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
   if (aborted(ctx)) return MSM_ERR_ABORTED;
   // --- accumulate
@@ -124,7 +159,12 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     k_accumulate<F><<<grid, tb, 0, st>>>(d_bases, line_stride, entries, bucket_start, g.NB,
                                          bucket_start + g.NB, pl.S, pl.n_slices, bucket_acc, partials);
     dim3 fgrid((g.NB + tb - 1) / tb, pl.n_lines);
-    k_fixup<F><<<fgrid, tb, 0, st>>>(bucket_start, g.NB, pl.S, pl.n_slices, bucket_acc, partials);
+    CU_TRY(ctx, cudaMemsetAsync(heavy_count, 0, (size_t)pl.n_lines * 4, st));
+    k_fixup<F><<<fgrid, tb, 0, st>>>(bucket_start, g.NB, pl.S, pl.n_slices, bucket_acc, partials, heavy_count,
+                                     heavy_list, heavy_cap);
+    dim3 hgrid(heavy_cap < 296 ? heavy_cap : 296, pl.n_lines);
+    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, pl.S, pl.n_slices, bucket_acc,
+                                                             partials, heavy_count, heavy_list, heavy_cap);
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[3], st));
   if (aborted(ctx)) return MSM_ERR_ABORTED;
@@ -134,8 +174,20 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     const uint64_t n_threads = (uint64_t)g.NB * pl.n_lines / pl.Q;
     k_bucket_reduce<F><<<(uint32_t)((n_threads + tb - 1) / tb), tb, tb * sizeof(Xyzz<F>), st>>>(
         bucket_acc, (uint32_t)n_threads, g.B, pl.Q, pl.RW, group_partials);
-    const uint32_t wt = g.W < 32 ? 32 : (g.W > 256 ? 256 : ((g.W + 31) / 32) * 32);
-    k_window_combine<F><<<pl.n_tasks, wt, (size_t)g.W * sizeof(Xyzz<F>), st>>>(group_partials, g.W, pl.PG, g.c, d_out);
+    const uint32_t Ws = pl.W_sets;
+    // the PG partials of every (task, window) group shrink 1024-fold per pass
+    uint32_t pg = pl.PG;
+    Xyzz<F>*src = group_partials, *dst = group_partials2;
+    while (pg > 8) {
+      const uint32_t out_pg = (pg + 1023) / 1024;
+      dim3 rgrid(out_pg, pl.n_tasks * Ws);
+      k_reduce_points<F><<<rgrid, tb, tb * sizeof(Xyzz<F>), st>>>(src, pg, out_pg, dst);
+      dc.launches += 1;
+      std::swap(src, dst);
+      pg = out_pg;
+    }
+    const uint32_t wt = Ws < 32 ? 32 : (Ws > 256 ? 256 : ((Ws + 31) / 32) * 32);
+    k_window_combine<F><<<pl.n_tasks, wt, (size_t)Ws * sizeof(Xyzz<F>), st>>>(src, Ws, pg, g.c, d_out);
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[4], st));
   dc.launches += 10;
@@ -171,8 +223,10 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   const uint32_t n_lines = (uint32_t)(bases->n / L);  // ag-cuda-ec/src/multiexp.rs:28-30
   DeviceCtx& dc = ctx->devs[0];
   CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const msm_bases::Shard& sh0 = bases->shards[0];
+  const bool use_table = sh0.table && num_chunks == 1 && n_lines == 1 && L == sh0.n && !ctx->window_override;
   Plan pl;
-  int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl);
+  int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0);
   if (rc) return rc;
   if (aborted(ctx)) return MSM_ERR_ABORTED;
   const uint32_t* d_scalars;
@@ -189,7 +243,7 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
     CU_TRY(ctx, cudaMemcpyAsync(ds, scalars, L * 32, cudaMemcpyHostToDevice, dc.stream));
     d_scalars = ds;
   }
-  rc = enqueue_msm<F>(ctx, dc, pl, static_cast<const PackedAffine<F>*>(bases->shards[0].ptr), (uint32_t)L,
+  rc = enqueue_msm<F>(ctx, dc, pl, static_cast<const PackedAffine<F>*>(use_table ? sh0.table : sh0.ptr), (uint32_t)L,
                       d_scalars, d_out, true);
   if (rc) {
     cudaStreamSynchronize(dc.stream);
@@ -228,9 +282,10 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
   }
   struct Job {
     size_t dev_idx;
-    const void* d_bases;  // resident (packed) device pointer
+    const void* d_bases;  // resident (packed) device pointer, or the shard's window table
     const char* h_bases;  // host pointer (API layout) when not resident
     size_t s_off, cnt;
+    uint32_t table_c;     // != 0: d_bases is a window table covering exactly cnt points
   };
   std::vector<Job> jobs;
   if (resident) {
@@ -238,16 +293,18 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
     for (const auto& sh : resident->shards) {
       const size_t lo = std::max(skip, sh.start), hi = std::min(skip + n, sh.start + sh.n);
       if (lo >= hi) continue;
-      jobs.push_back({(size_t)sh.dev_idx,
-                      static_cast<const char*>(sh.ptr) + (lo - sh.start) * sizeof(PackedAffine<F>), nullptr,
-                      lo - skip, hi - lo});
+      const bool whole = sh.table && lo == sh.start && hi == sh.start + sh.n && !ctx->window_override;
+      if (whole) jobs.push_back({(size_t)sh.dev_idx, sh.table, nullptr, lo - skip, hi - lo, sh.table_c});
+      else jobs.push_back({(size_t)sh.dev_idx,
+                           static_cast<const char*>(sh.ptr) + (lo - sh.start) * sizeof(PackedAffine<F>), nullptr,
+                           lo - skip, hi - lo, 0u});
     }
   } else {
     const size_t chunk = (n + n_dev - 1) / n_dev;  // ec-gpu-proxy/src/multiexp.rs:329-337
     for (size_t d = 0; d * chunk < n; d++) {
       const size_t cnt = std::min(chunk, n - d * chunk);
       jobs.push_back({d, nullptr, static_cast<const char*>(host_bases) + d * chunk * sizeof(ApiAffine<F>),
-                      d * chunk, cnt});
+                      d * chunk, cnt, 0u});
     }
   }
   std::vector<int> rcs(jobs.size(), MSM_OK);
@@ -267,7 +324,7 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
     shadow.curve = ctx->curve;
     shadow.window_override = ctx->window_override;
     shadow.abort_flag = ctx->abort_flag;
-    int rc = make_plan<F>(&shadow, (uint32_t)job.cnt, 1, 1, plans[j]);
+    int rc = make_plan<F>(&shadow, (uint32_t)job.cnt, 1, 1, plans[j], job.table_c);
     if (rc) {
       rcs[j] = rc;
       return;
@@ -354,6 +411,46 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
   }
   for (size_t j = 0; j < jobs.size(); j++)
     if (jobs[j].dev_idx == 0) collect_timings(ctx, d0, plans[j], true);
+  return MSM_OK;
+}
+
+// Window table for one resident shard (msm_bases_precompute).
+template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint32_t c) {
+  if (sh.n == 0) return MSM_OK;
+  DeviceCtx& dc = ctx->devs[sh.dev_idx];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const uint32_t bits = scalar_bits(ctx->curve);
+  if (c == 0) {
+    // all windows share one bucket set: cost = W * n mixed adds + 2^(c-1) * 2 full adds
+    double best = 1e300;
+    for (uint32_t cc = 11; cc <= 24; cc++) {
+      const uint32_t W = (bits + 1 + cc - 1) / cc;
+      if ((uint64_t)W * sh.n >= (1ull << 31)) continue;
+      const double cost = (double)W * (double)sh.n * 10.0 + (double)(1u << (cc - 1)) * 34.0;
+      if (cost < best) {
+        best = cost;
+        c = cc;
+      }
+    }
+    if (c == 0) return MSM_ERR_TOO_LARGE;
+  }
+  const uint32_t W = (bits + 1 + c - 1) / c;
+  if (c < 11 || c > 24 || W > TABLE_MAX_W || (uint64_t)W * sh.n >= (1ull << 31)) {
+    set_error(ctx, "msm_bases_precompute: window size out of range for this shard");
+    return MSM_ERR_INVALID;
+  }
+  if (sh.table) {
+    cudaFree(sh.table);
+    sh.table = nullptr;
+  }
+  CU_TRY(ctx, cudaMalloc(&sh.table, (size_t)W * sh.n * sizeof(PackedAffine<F>)));
+  k_build_tables<F><<<(uint32_t)((sh.n + 63) / 64), 64, 0, dc.stream>>>(
+      static_cast<const PackedAffine<F>*>(sh.ptr), (uint32_t)sh.n, c, W, static_cast<PackedAffine<F>*>(sh.table));
+  dc.launches += 1;
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  sh.table_c = c;
+  sh.table_W = W;
   return MSM_OK;
 }
 
@@ -493,6 +590,7 @@ template <class F> FieldOps make_field_ops(const char* name) {
   o.multiple_multiexp = &multiple_multiexp_impl<F>;
   o.multiexp = &multiexp_impl<F>;
   o.convert_bases = &convert_bases_impl<F>;
+  o.build_table = &build_table_impl<F>;
   o.synth_points = &synth_points_impl<F>;
   o.test_fq = &test_fq_impl<F>;
   o.test_ec = &test_ec_impl<F>;

@@ -208,6 +208,92 @@ template <class P> MSM_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Carry-save variant of the same product.  On B200 the carry-in form IMAD.WIDE.U32.X holds the
+// multiplier pipe for twice as long as a carry-free IMAD.WIDE.U32 (tools/imad_peak.cu,
+// profiles/r01_imad_peak_v2.json), and a field product is ~100 of them.  Here NO multiply takes a
+// carry in: each wide multiply-add's carry OUT is counted (one IADD3.X on the otherwise idle ALU
+// pipe) in a small counter attached to the limb two positions up, and the counters are folded in
+// once per product.  Same even/odd accumulators and the same invariant as mont_row above; cE[k] /
+// cO[k] = pending carries into E[k] / O[k].  Counters never exceed 4N.
+// ---------------------------------------------------------------------------------------------
+template <class P, bool FIRST>
+MSM_HD void mont_row_cs(uint32_t* E, uint32_t* O, uint32_t* cE, uint32_t* cO, const uint32_t* a, uint32_t bi) {
+  constexpr int N = P::N;
+  // on entry (non-first): E/cE are last row's O/cO; O/cO are last row's E/cE, still unshifted
+  if (FIRST) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      mul_wide(E[j], E[j + 1], a[j], bi);
+      mul_wide(O[j], O[j + 1], a[j + 1], bi);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) cE[j] = cO[j] = 0;
+  } else {
+    // orphan limb O[1] (and the carries still pending into it) joins the new E[0]; their carries
+    // are pending into E[1]
+    uint32_t c1 = cE[1];
+    add_cs(E[0], c1, cE[0]);  // carries that were pending into this limb while it was O[0]
+    add_cs(E[0], c1, O[1]);
+    add_cs(E[0], c1, cO[1]);
+    cE[0] = 0;
+    cE[1] = c1;
+    // shift the old E (now O) down by two limbs while adding the odd products: new O[j] = old
+    // O[j+2] and new cO[j] = old cO[j+2] (nothing ever carries into limb 0); the product
+    // a[j+1]*bi lands on the pair (j, j+1) and its carry on limb j+2
+    uint32_t nO[N], ncO[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) ncO[j] = j + 2 < N ? cO[j + 2] : 0;
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) mad_wide_cs3(nO[j], nO[j + 1], ncO[j + 2], a[j + 1], bi, O[j + 2], O[j + 3]);
+    mul_wide(nO[N - 2], nO[N - 1], a[N - 1], bi);
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      O[j] = nO[j];
+      cO[j] = ncO[j];
+    }
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) mad_wide_cs(E[j], E[j + 1], cE[j + 2], a[j], bi);
+    mad_wide_cs(E[N - 2], E[N - 1], cO[N - 1], a[N - 2], bi);  // weight 2^(32N) = limb O[N-1]
+  }
+  const uint32_t m = mul_lo(E[0], P::INV);
+#pragma unroll
+  for (int j = 0; j < N - 2; j += 2) mad_wide_cs(O[j], O[j + 1], cO[j + 2], P::P(j + 1), m);
+  {
+    uint32_t never = 0;  // the top pair cannot overflow (T < 2^(32(N+1)))
+    mad_wide_cs(O[N - 2], O[N - 1], never, P::P(N - 1), m);
+  }
+#pragma unroll
+  for (int j = 0; j < N - 2; j += 2) mad_wide_cs(E[j], E[j + 1], cE[j + 2], P::P(j), m);
+  mad_wide_cs(E[N - 2], E[N - 1], cO[N - 1], P::P(N - 2), m);
+}
+
+template <class P> MSM_HD Fp<P> fp_mul_cs(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  uint32_t X[N], Y[N], cX[N], cY[N];
+  mont_row_cs<P, true>(X, Y, cX, cY, a.v, b.v[0]);
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    mont_row_cs<P, false>(Y, X, cY, cX, a.v, b.v[i]);
+    if (i + 1 < N) mont_row_cs<P, false>(X, Y, cX, cY, a.v, b.v[i + 1]);
+  }
+  // last row had E = Y, O = X:  result = (E >> 32) + O + pending carries (cE[k+1] + cO[k] into limb k)
+  Fp<P> r;
+  r.v[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
+  r.v[N - 1] = addc(X[N - 1], 0u);
+  uint32_t cnt[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) cnt[k] = cX[k] + (k + 1 < N ? cY[k + 1] : 0u);
+  r.v[0] = add_cc(r.v[0], cnt[0]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(r.v[k], cnt[k]);
+  r.v[N - 1] = addc(r.v[N - 1], cnt[N - 1]);
+  fp_csub_p<P>(r.v);
+  return r;
+}
+
 template <class P> MSM_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
 
 // Montgomery <-> canonical
@@ -248,7 +334,8 @@ template <class P> MSM_COLD Fp<P> fp_inv(const Fp<P>& a) {
 // ---------------------------------------------------------------------------------------------
 namespace msm {
 
-template <class P> struct FieldSat {
+// CS = true: products use the carry-save form fp_mul_cs.
+template <class P, bool CS = false> struct FieldSat {
   static constexpr int N = P::N;
   static constexpr int API_WORDS = P::N;     // words per element at the API boundary
   static constexpr int PACKED_WORDS = P::N;  // words per resident-base coordinate
@@ -262,8 +349,8 @@ template <class P> struct FieldSat {
   template <int K, int LM> static MSM_HD Elem neg(const Elem& a) { return fp_neg<P>(a); }
   static MSM_HD Elem norm(const Elem& a) { return a; }
   template <int LO, int HI> static MSM_HD bool is_multiple_of_p(const Elem& a) { return fp_is_zero<P>(a); }
-  static MSM_HD Elem mul(const Elem& a, const Elem& b) { return fp_mul<P>(a, b); }
-  static MSM_HD Elem sqr(const Elem& a) { return fp_sqr<P>(a); }
+  static MSM_HD Elem mul(const Elem& a, const Elem& b) { return CS ? fp_mul_cs<P>(a, b) : fp_mul<P>(a, b); }
+  static MSM_HD Elem sqr(const Elem& a) { return mul(a, a); }
   static MSM_HD Elem inv(const Elem& a) { return fp_inv<P>(a); }
 
   // resident-base coordinate <-> registers (same layout as the API: nothing to do)
@@ -276,6 +363,10 @@ template <class P> struct FieldSat {
   static MSM_HD void api_to_packed(const uint32_t* api, uint32_t* packed) {
 #pragma unroll
     for (int i = 0; i < N; i++) packed[i] = api[i];
+  }
+  static MSM_HD void to_packed(const Elem& a, uint32_t* packed) {
+#pragma unroll
+    for (int i = 0; i < N; i++) packed[i] = a.v[i];
   }
   static MSM_HD Elem from_api(const uint32_t* w) { return unpack(w); }
   static MSM_HD void to_api(const Elem& a, uint32_t* w) {

@@ -28,8 +28,10 @@ struct Geometry {
   uint32_t c;          // window bits
   uint32_t W;          // windows
   uint32_t B;          // buckets per (task, window) = 2^(c-1)
-  uint32_t NB;         // num_chunks * W * B
+  uint32_t NB;         // num_chunks * W * B   (folded: B)
   uint32_t scalar_bits;
+  uint32_t fold;       // 1: bases are a window table T[w][i] = 2^(c w) P_i, all windows share one bucket set
+  uint32_t table_stride;  // points per window in the table (= L)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -82,9 +84,12 @@ MSM_D void load_scalar(const uint32_t* scalars, uint32_t i, uint32_t k[8]) {
 }
 
 // SCATTER = false: counts[g]++ ;  SCATTER = true: entries[cursor[g]++] = i | sign<<31
+// g_lo / g_hi: only digits whose bucket id lies in [g_lo, g_hi) are handled; the scatter runs in
+// several such passes so that the randomly written slice of `entries` stays resident in the L2.
 template <bool SCATTER>
 __global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
-                         uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
+                         uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries,
+                         uint32_t g_lo, uint32_t g_hi) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= geo.L) return;
   uint32_t k[8];
@@ -92,12 +97,33 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
   const uint32_t task = i / geo.chunk_len;
   const uint32_t base = task * geo.W;
   for_each_digit(k, geo.c, geo.W, [&](uint32_t w, uint32_t bucket, bool neg) {
-    const uint32_t g = (base + w) * geo.B + (bucket - 1);
+    const uint32_t g = geo.fold ? (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+    if (g < g_lo || g >= g_hi) return;
+    // The top window only carries the few leftover scalar bits, so all points share a handful of
+    // its buckets: aggregate those atomics per warp (one atomic per distinct bucket).
+    uint32_t rank = 0, total = 1, leader_lane = 0;
+    const bool aggregate = (w + 1 == geo.W);
+    uint32_t peers = 0;
+    if (aggregate) {
+      peers = __match_any_sync(__activemask(), g);
+      leader_lane = __ffs(peers) - 1;
+      total = __popc(peers);
+      rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
+    }
     if (SCATTER) {
-      const uint32_t pos = atomicAdd(&counts_or_cursor[g], 1u);
-      entries[pos] = i | (neg ? 0x80000000u : 0u);
+      uint32_t pos;
+      if (aggregate) {
+        uint32_t base_pos = 0;
+        if ((threadIdx.x & 31) == leader_lane) base_pos = atomicAdd(&counts_or_cursor[g], total);
+        pos = __shfl_sync(peers, base_pos, leader_lane) + rank;
+      } else {
+        pos = atomicAdd(&counts_or_cursor[g], 1u);
+      }
+      const uint32_t idx = geo.fold ? w * geo.table_stride + i : i;
+      entries[pos] = idx | (neg ? 0x80000000u : 0u);
     } else {
-      atomicAdd(&counts_or_cursor[g], 1u);
+      if (!aggregate) atomicAdd(&counts_or_cursor[g], 1u);
+      else if ((threadIdx.x & 31) == leader_lane) atomicAdd(&counts_or_cursor[g], total);
     }
   });
 }
@@ -283,11 +309,29 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
   }
 }
 
+// Block-wide sum of one XYZZ value per thread (blockDim.x <= 128, power of two); result in thread 0.
+template <class F> MSM_D Xyzz<F> block_sum_xyzz(Xyzz<F> v, Xyzz<F>* sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (uint32_t stride = blockDim.x >> 1; stride >= 1; stride >>= 1) {
+    if (threadIdx.x < stride) {
+      v = xyzz_add<F>(v, sh[threadIdx.x + stride]);
+      sh[threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+  return v;
+}
+
 // One thread per bucket: empty -> infinity; cut by slice boundaries -> sum of its partial slots.
+// Buckets spread over more than HEAVY_SPAN slices (skewed scalars; the short top window of a
+// folded table) go to a work list that k_fixup_heavy reduces with one block each.
+constexpr uint32_t HEAVY_SPAN = 16;
 template <class F>
 __global__ void __launch_bounds__(128)
 k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
-        Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials) {
+        Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials,
+        uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list, uint32_t heavy_cap) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= NB) return;
   const uint32_t line = blockIdx.y;
@@ -300,9 +344,53 @@ k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint
   }
   const uint32_t t0 = start / S, t1 = (end - 1) / S;
   if (t0 == t1) return;  // written directly by k_accumulate
+  if (t1 - t0 > HEAVY_SPAN) {
+    const uint32_t slot = atomicAdd(&heavy_count[line], 1u);
+    if (slot < heavy_cap) heavy_list[(size_t)line * heavy_cap + slot] = g;  // cap = n_slices/HEAVY_SPAN + 1 cannot overflow
+    return;
+  }
   Xyzz<F> acc = load_vec(&partials[2 * t0 + 1]);
   for (uint32_t t = t0 + 1; t <= t1; t++) acc = xyzz_add<F>(acc, load_vec(&partials[2 * t]));
   store_vec(&bucket_acc[g], acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_fixup_heavy(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
+              Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials,
+              const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list, uint32_t heavy_cap) {
+  extern __shared__ uint4 smem_raw[];
+  Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw);
+  const uint32_t line = blockIdx.y;
+  bucket_acc += (size_t)line * NB;
+  partials += (size_t)line * 2 * n_slices;
+  const uint32_t count = min(heavy_count[line], heavy_cap);
+  for (uint32_t item = blockIdx.x; item < count; item += gridDim.x) {
+    const uint32_t g = heavy_list[(size_t)line * heavy_cap + item];
+    const uint32_t t0 = bucket_start[g] / S, t1 = (bucket_start[g + 1] - 1) / S;
+    // element 0 = slot 2*t0+1, element k = slot 2*(t0+k), k = 1 .. t1-t0
+    Xyzz<F> acc = xyzz_inf<F>();
+    for (uint32_t k = threadIdx.x; k <= t1 - t0; k += blockDim.x)
+      acc = xyzz_add<F>(acc, load_vec(k == 0 ? &partials[2 * t0 + 1] : &partials[2 * (t0 + k)]));
+    acc = block_sum_xyzz<F>(acc, sh);
+    if (threadIdx.x == 0) store_vec(&bucket_acc[g], acc);
+    __syncthreads();
+  }
+}
+
+// Plain sum of `count` consecutive points per group, 1024 per block: out[group][ceil(count/1024)].
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce_points(const Xyzz<F>* __restrict__ in, uint32_t count, uint32_t out_count, Xyzz<F>* __restrict__ out) {
+  extern __shared__ uint4 smem_raw[];
+  Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw);
+  const uint32_t group = blockIdx.y, chunk = blockIdx.x;
+  const Xyzz<F>* src = in + (size_t)group * count;
+  const uint32_t lo = chunk * 1024, hi = min(lo + 1024, count);
+  Xyzz<F> acc = xyzz_inf<F>();
+  for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) acc = xyzz_add<F>(acc, load_vec(&src[k]));
+  acc = block_sum_xyzz<F>(acc, sh);
+  if (threadIdx.x == 0) store_vec(&out[(size_t)group * out_count + chunk], acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -379,6 +467,58 @@ __global__ void k_convert_bases(const ApiAffine<F>* __restrict__ in, uint32_t n,
   F::api_to_packed(a.x, o.x);  // identity (0,0) stays all-zero
   F::api_to_packed(a.y, o.y);
   out[i] = o;
+}
+
+// Window table for resident bases: T[w][i] = 2^(c w) * P_i in the packed affine layout, w < W.
+// One thread per point: (W-1)*c doublings in XYZZ, then one shared inversion (Montgomery's trick
+// over the thread's W-1 results).  With the table every window of a large MSM lands in ONE bucket
+// set: no per-window bucket arrays and no Horner doublings at the end of each call.
+constexpr int TABLE_MAX_W = 24;
+template <class F>
+__global__ void __launch_bounds__(64)
+k_build_tables(const PackedAffine<F>* __restrict__ bases, uint32_t n, uint32_t c, uint32_t W,
+               PackedAffine<F>* __restrict__ table) {
+  using E = typename F::Elem;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PackedAffine<F> src = bases[i];
+  table[i] = src;
+  Affine<F> p;
+  p.x = F::unpack(src.x);
+  p.y = F::unpack(src.y);
+  PackedAffine<F> zero;
+  for (int k = 0; k < F::PACKED_WORDS; k++) zero.x[k] = zero.y[k] = 0;
+  if (aff_is_identity<F>(p)) {
+    for (uint32_t w = 1; w < W; w++) table[(size_t)w * n + i] = zero;
+    return;
+  }
+  Xyzz<F> cur;
+  cur.x = p.x;
+  cur.y = p.y;
+  cur.zz = F::one();
+  cur.zzz = F::one();
+  Xyzz<F> pts[TABLE_MAX_W];
+  E pref[TABLE_MAX_W];
+  E prod = F::one();
+  for (uint32_t w = 1; w < W; w++) {
+    for (uint32_t k = 0; k < c; k++) cur = xyzz_dbl<F>(cur);
+    pts[w] = cur;
+    pref[w] = prod;
+    if (!xyzz_is_inf<F>(cur)) prod = F::mul(prod, F::mul(cur.zz, cur.zzz));
+  }
+  E inv = F::inv(prod);
+  for (uint32_t w = W - 1; w >= 1; w--) {
+    if (xyzz_is_inf<F>(pts[w])) {
+      table[(size_t)w * n + i] = zero;
+      continue;
+    }
+    const E zi = F::mul(inv, pref[w]);  // 1 / (zz*zzz)
+    inv = F::mul(inv, F::mul(pts[w].zz, pts[w].zzz));
+    PackedAffine<F> o;
+    F::to_packed(F::mul(pts[w].x, F::mul(zi, pts[w].zzz)), o.x);
+    F::to_packed(F::mul(pts[w].y, F::mul(zi, pts[w].zz)), o.y);
+    table[(size_t)w * n + i] = o;
+  }
 }
 
 template <class F>

@@ -87,6 +87,24 @@ MSM_D void madc_wide_0(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b) {
                : "r"(a), "r"(b));
 }
 MSM_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+// carry-save forms: the wide multiply-add takes no carry in; its carry out is counted in `cnt`
+// (lo,hi) += a*b ; cnt += carry                     -> IMAD.WIDE.U32 (carry-out) + IADD3.X
+MSM_D void mad_wide_cs(uint32_t& lo, uint32_t& hi, uint32_t& cnt, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+               : "+r"(lo), "+r"(hi), "+r"(cnt)
+               : "r"(a), "r"(b));
+}
+// (dlo,dhi) = a*b + (clo,chi) ; cnt += carry
+MSM_D void mad_wide_cs3(uint32_t& dlo, uint32_t& dhi, uint32_t& cnt, uint32_t a, uint32_t b, uint32_t clo,
+                        uint32_t chi) {
+  asm volatile("mad.lo.cc.u32 %0, %3, %4, %5;\n\tmadc.hi.cc.u32 %1, %3, %4, %6;\n\taddc.u32 %2, %2, 0;"
+               : "=r"(dlo), "=r"(dhi), "+r"(cnt)
+               : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+// x += y ; cnt += carry
+MSM_D void add_cs(uint32_t& x, uint32_t& cnt, uint32_t y) {
+  asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(x), "+r"(cnt) : "r"(y));
+}
 
 #else
 // ---------------------------------------------------------------- host: emulated carry flag
@@ -150,6 +168,24 @@ inline void madc_wide_0(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b) {
   dhi = (uint32_t)(s >> 32);
 }
 inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline void mad_wide_cs(uint32_t& lo, uint32_t& hi, uint32_t& cnt, uint32_t a, uint32_t b) {
+  unsigned __int128 s = (unsigned __int128)((uint64_t)a * b) + (((uint64_t)hi << 32) | lo);
+  lo = (uint32_t)s;
+  hi = (uint32_t)(s >> 32);
+  cnt += (uint32_t)(s >> 64);
+}
+inline void mad_wide_cs3(uint32_t& dlo, uint32_t& dhi, uint32_t& cnt, uint32_t a, uint32_t b, uint32_t clo,
+                         uint32_t chi) {
+  unsigned __int128 s = (unsigned __int128)((uint64_t)a * b) + (((uint64_t)chi << 32) | clo);
+  dlo = (uint32_t)s;
+  dhi = (uint32_t)(s >> 32);
+  cnt += (uint32_t)(s >> 64);
+}
+inline void add_cs(uint32_t& x, uint32_t& cnt, uint32_t y) {
+  uint64_t s = (uint64_t)x + y;
+  x = (uint32_t)s;
+  cnt += (uint32_t)(s >> 32);
+}
 #endif
 
 }  // namespace msm

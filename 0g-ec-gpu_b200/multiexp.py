@@ -73,6 +73,14 @@ class DeviceData:
     def num_points(self) -> int:
         return load_library().msm_bases_num_points(self._h)
 
+    def precompute(self, window_bits: int = 0) -> int:
+        """Engine extension (msm_bases_precompute): build the window table for repeated large
+        single MSMs over these bases.  Returns the table's window size."""
+        lib = load_library()
+        check(lib.msm_bases_precompute(self.workspace.handle, self._h, window_bits), self.workspace.handle,
+              cuda_style=True)
+        return lib.msm_bases_table_window(self._h)
+
     def free(self):
         if self._h:
             load_library().msm_bases_free(self._h)

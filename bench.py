@@ -1,0 +1,365 @@
+#!/usr/bin/env python3
+"""bench.py -- BN254 G1 MSM throughput (BASELINE.json: "BN254 G1 MSM points/sec (2^24, 1/2/4/8 B200)
++ % IMAD roofline vs host CPU").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 24] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one complete MSM of 2^log_n synthetic points (seed 0x0badc0de).
+With N GPUs the point/scalar arrays are split into N contiguous shards (the partition of
+MultiexpKernel::parallel_multiexp, ec-gpu-proxy/src/multiexp.rs:329-337), each rank computes one
+partial point, the N partials (96 bytes each) are all-gathered over NCCL/NVLink and summed on the
+device.  Total work is fixed => "scaling": "strong".
+
+  value     whole-job points/s with bases AND scalars resident in HBM (msm_multiple_multiexp_device)
+  e2e       the same through the reference-facing call with HOST scalars (pinned) and a host result:
+            msm_multiple_multiexp == ag_cuda_ec::multiple_multiexp (bases resident, as in that API)
+  roofline  the dominant kernel (k_accumulate, bucket accumulation) against the int32-multiply
+            (IMAD) pipe: algorithmic MACs per launch = n * 21760 (16 windows x 10 field products x
+            136 MACs) / its CUDA-event time on the launching stream
+  cpu_baseline  the oracle's restatement of the reference's multiexp_cpu on the host cores, on a
+            bounded sample (the only place this file touches oracle/ besides --impl reference)
+
+Timing: CUDA events on the stream every kernel is launched on (the engine is switched onto torch's
+current stream), barrier + synchronize on both sides, max over ranks.  Inputs per step (1 GiB of
+bases, 0.5 GiB of scalars, >= 0.8 GiB of sorted digits) exceed the 126 MB L2 many times over.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 0x0BADC0DE
+MACS_PER_POINT = {0: 16 * 10 * 136, 1: 16 * 10 * 300}  # SURVEY.md section 8d / BASELINE.md section 3
+IMAD_PEAK_NOMINAL = 148 * 64 * 1.965e9  # MAC/s; tools/imad_peak.cu measured 1.852e13 (99.5 %) on this pool
+METRIC = {0: "BN254 G1 MSM points/sec", 1: "BLS12-381 G1 MSM points/sec"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+
+        def num(s):
+            try:
+                return float(s)
+            except ValueError:
+                return None
+
+        rows = [r for r in self.rows if len(r) >= 7 and num(r[0]) is not None]
+        sm = [num(r[0]) for r in rows]
+        mx = [num(r[1]) for r in rows if num(r[1]) is not None]
+        pw = [num(r[2]) or 0.0 for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        busy = [c for c, p in zip(sm, pw) if p > 250] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def cpu_baseline(curve, log_sample, threads=None):
+    """The oracle's multiexp_cpu (restatement of ec-gpu-proxy/src/multiexp_cpu.rs:244-367) on the
+    host cores: a reported baseline, not the target."""
+    from oracle import oracle as O
+
+    O.build()
+    n = 1 << log_sample
+    threads = threads or O.ncores()
+    pts = O.gen_points(curve, SEED, n)
+    sc = O.gen_scalars(curve, SEED, n)
+    t0 = time.perf_counter()
+    O.multiexp_cpu(curve, pts, sc, nthreads=threads)
+    dt = time.perf_counter() - t0
+    c = O.window_for(n)
+    bits = 254 if curve == 0 else 255
+    windows = (bits + c - 1) // c
+    return {"value": n / dt, "unit": "points/s", "cores": min(threads, windows), "kind": "port",
+            "host_threads": threads, "seconds": round(dt, 3),
+            "sample": "one multiexp_cpu call on the first 2^%d points of the same synthetic workload "
+                      "(c = %d, %d windows, one thread per window as the reference's rayon loop)" % (log_sample, c, windows)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU multiexp (oracle port; the Rust original cannot be built
+    here: no Rust toolchain, arkworks not vendored) with all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    O.build()
+    curve = args.curve
+    log_s = min(args.log_n, args.ref_log_sample)
+    n = 1 << log_s
+    pts = O.gen_points(curve, SEED, n)
+    sc = O.gen_scalars(curve, SEED, n)
+    threads = O.ncores()
+    for _ in range(args.warmup):
+        O.multiexp_cpu(curve, pts[: max(n // 8, 1)], sc[: max(n // 8, 1)], nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.multiexp_cpu(curve, pts, sc, nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    c = O.window_for(n)
+    bits = 254 if curve == 0 else 255
+    windows = (bits + c - 1) // c
+    name = "BN254 G1" if curve == 0 else "BLS12-381 G1"
+    sample = ("each step = one multiexp_cpu call on the first 2^%d of the 2^%d synthetic points "
+              "(c = %d, %d windows = usable threads)" % (log_s, args.log_n, c, windows))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC[curve], "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "%s MSM 2^%d (reference CPU multiexp, bounded sample per step)" % (name, args.log_n),
+                   "log_n": args.log_n, "sample_log_n": log_s, "seed": SEED},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": min(threads, windows),
+                         "host_threads": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def to_affine_bytes(lib, h, jac, fq):
+    import numpy as np
+
+    xy = np.zeros(2 * fq, dtype=np.uint8)
+    inf = np.zeros(1, dtype=np.uint8)
+    assert lib.msm_to_affine(h, jac.ctypes.data, 1, 0, xy.ctypes.data, inf.ctypes.data) == 0
+    return np.concatenate([xy, inf])
+
+
+def spot_check(m, curve, device):
+    """Untimed: a 2^14-point MSM of the same synthetic stream through the public API equals the
+    oracle's result bit-exactly (canonical affine)."""
+    from oracle import oracle as O
+
+    n = 1 << 14
+    pts, sc = O.gen_points(curve, SEED, n), O.gen_scalars(curve, SEED, n)
+    kern = m.MultiexpKernel.create([device], curve)
+    got = kern.multiexp(m.Worker(), pts, sc, 0)
+    want = O.multiexp_cpu(curve, pts, sc)
+    ga, gi = O.to_affine(curve, got)
+    wa, wi = O.to_affine(curve, want)
+    return bool((ga == wa).all() and (gi == wi).all())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--curve", type=int, default=0, help="0 = BN254 G1 (headline), 1 = BLS12-381 G1")
+    ap.add_argument("--cpu-log-sample", type=int, default=21, help="cpu_baseline sample size (log2)")
+    ap.add_argument("--ref-log-sample", type=int, default=20, help="--impl reference sample per step (log2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-table", action="store_true",
+                    help="skip msm_bases_precompute (window table next to the resident bases)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if rank == 0:
+            print("bench.py: --gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d"
+                  % (args.gpus, world, args.gpus), file=sys.stderr)
+        sys.exit(2)
+
+    import torch
+    import torch.distributed as dist
+
+    import ec_gpu_b200 as m
+
+    lib = m.load_library()  # ImportError if the CUDA library is missing: there is no fallback
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    curve = args.curve
+    fq = m.fq_bytes(curve)
+    ws = m.Workspace(curve, devices=[local_rank])
+    h = ws.handle
+    stream = torch.cuda.current_stream()
+    assert lib.msm_set_stream(h, ctypes.c_void_p(stream.cuda_stream)) == 0
+
+    n_total = 1 << args.log_n
+    n_local = n_total // world
+    start = rank * n_local
+    d_pts = torch.empty(n_local * 2 * fq, dtype=torch.uint8, device=dev)
+    d_sc = torch.empty(n_local * 32, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(3 * fq, dtype=torch.uint8, device=dev)
+    d_gather = torch.zeros(world * 3 * fq, dtype=torch.uint8, device=dev)
+    d_final = torch.zeros(3 * fq, dtype=torch.uint8, device=dev)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    assert lib.msm_synth_points_device(h, SEED, start, n_local, ptr(d_pts)) == 0
+    assert lib.msm_synth_scalars_device(h, SEED, start, n_local, ptr(d_sc)) == 0
+    bases = ctypes.c_void_p()
+    t_setup = time.perf_counter()
+    rc = lib.msm_bases_from_device(h, ptr(d_pts), n_local, ctypes.byref(bases))
+    assert rc == 0, lib.msm_last_error(h)
+    if not args.no_table:
+        # part of making the bases resident (untimed, like upload_multiexp_bases in the reference API)
+        rc = lib.msm_bases_precompute(h, bases, 0)
+        assert rc == 0, lib.msm_last_error(h)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    del d_pts
+    torch.cuda.empty_cache()
+    h_sc = torch.empty(n_local * 32, dtype=torch.uint8, pin_memory=True)
+    h_sc.copy_(d_sc)
+    h_out = torch.zeros(3 * fq, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def combine():
+        if world > 1:
+            dist.all_gather_into_tensor(d_gather, d_out)
+            if rank == 0:
+                assert lib.msm_sum_points_device(h, ptr(d_gather), world, ptr(d_final)) == 0
+        else:
+            d_final.copy_(d_out)
+
+    acc_ms = []
+
+    def step_device():
+        rc = lib.msm_multiple_multiexp_device(h, bases, ptr(d_sc), n_local, 1, ptr(d_out))
+        assert rc == 0, lib.msm_last_error(h)
+        acc_ms.append(ws.timings()["accumulate_ms"])
+        combine()
+
+    def step_e2e():
+        rc = lib.msm_multiple_multiexp(h, bases, ctypes.c_void_p(h_sc.data_ptr()), n_local, 1, 8, 1,
+                                       ctypes.c_void_p(h_out.data_ptr()))
+        assert rc == 0, lib.msm_last_error(h)
+        if world > 1:
+            d_out.copy_(h_out, non_blocking=True)
+            combine()
+            if rank == 0:
+                h_out.copy_(d_final)
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks
+
+    launches0 = None
+    # warm-up happens inside timed(); launches are counted over the timed steps only
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = ws.timings()["kernel_launches"]
+    del acc_ms[:]
+    ms_dev, clocks = timed(step_device, args.steps, 0, sample_clocks=True)
+    acc_timed = list(acc_ms)
+    t_last = ws.timings()
+    launches = t_last["kernel_launches"] - launches0
+    result_dev = d_final.cpu().numpy().copy() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
+    result_e2e = h_out.numpy().copy() if rank == 0 else None
+
+    if rank == 0:
+        value = n_total * args.steps / (ms_dev * 1e-3)
+        e2e = n_total * args.steps / (ms_e2e * 1e-3)
+        # dominant kernel: bucket accumulation of this rank's shard
+        acc_avg_ms = sum(acc_timed) / len(acc_timed)
+        macs = n_local * MACS_PER_POINT[curve]
+        achieved = macs / (acc_avg_ms * 1e-3)
+        roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved / 1e12,
+                    "peak": IMAD_PEAK_NOMINAL / 1e12, "unit": "TMAC/s", "frac": achieved / IMAD_PEAK_NOMINAL,
+                    "traffic": None, "avg_kernel_ms": acc_avg_ms, "algorithmic_macs_per_launch": macs,
+                    "peak_source": "148 SMs x 64 int32-multiply lanes/clk x 1.965 GHz; tools/imad_peak.cu measured "
+                                   "1.852e13 MAC/s (99.5 % of it) on this pool; MEASURED_PEAKS.json has no integer figure",
+                    "whole_step_frac": value / world * MACS_PER_POINT[curve] / IMAD_PEAK_NOMINAL}
+        same = bool((to_affine_bytes(lib, h, result_dev, fq) == to_affine_bytes(lib, h, result_e2e, fq)).all())
+        name = "BN254 G1" if curve == 0 else "BLS12-381 G1"
+        out = {
+            "metric": METRIC[curve], "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "%s MSM 2^%d, contiguous shards of 2^%d points per GPU (BASELINE.json configs[2])"
+                                   % (name, args.log_n, n_local.bit_length() - 1),
+                       "log_n": args.log_n, "points_per_gpu": n_local, "window_bits": t_last["window_bits"],
+                       "num_windows": t_last["num_windows"], "field_impl": lib.msm_field_impl(h).decode(),
+                       "seed": SEED,
+                       "window_table": (not args.no_table), "table_window_bits": int(lib.msm_bases_table_window(bases)),
+                       "resident_setup_s": round(setup_s, 3),
+                       "l2": "per-step inputs (bases %d MiB + scalars %d MiB + sorted digits) exceed the 126 MB L2"
+                             % (n_local * 2 * fq >> 20, n_local * 32 >> 20)},
+            "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": n_total * 32, "d2h_bytes_per_step": world * 3 * fq,
+                    "call": "msm_multiple_multiexp: host scalars (pinned) in, host point out; bases resident as in "
+                            "ag_cuda_ec::multiple_multiexp"},
+            "gpu_launches": int(launches + (args.steps if world > 1 else 0)),
+            "roofline": roofline,
+            "phases_ms": {k: round(t_last[k], 3) for k in ("sort_ms", "accumulate_ms", "reduce_ms", "total_ms")},
+            "clocks": clocks,
+            "paths_agree": same,
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(curve, min(args.cpu_log_sample, args.log_n))
+            out["spot_check_vs_oracle"] = spot_check(m, curve, local_rank)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,16 @@ int msm_bases_upload_sharded(msm_ctx* ctx, const void* xy_mont, size_t n_points,
 /* Same as msm_bases_upload with the source points already in device memory of device 0 (same
  * {x,y} Montgomery layout); the engine keeps its own resident copy, the source may be freed. */
 int msm_bases_from_device(msm_ctx* ctx, const void* d_xy_mont, size_t n_points, msm_bases** out);
+/* Optional, for bases that serve repeated LARGE single MSMs (num_chunks == 1, one line, all
+ * points of a shard): build the window table T[w][i] = 2^(c w) P_i next to the resident copy
+ * (W = ceil((bits+1)/c) times its size; window_bits == 0 lets the engine choose c).  Calls that
+ * cover a whole shard then use one shared bucket set for all windows -- no per-window bucket
+ * arrays, no Horner doublings; every other call shape keeps using the plain resident copy.
+ * Pure optimisation: results are unchanged.  The reference has no counterpart (its kernel walks
+ * the windows of each scalar in separate threads, ag-build/cl/multiexp.cl:95-119). */
+int msm_bases_precompute(msm_ctx* ctx, msm_bases* b, uint32_t window_bits);
+/* Window size of the table (0: none). */
+uint32_t msm_bases_table_window(const msm_bases* b);
 /* DeviceData::size (ag-cuda-proxy/src/params.rs:209): bytes. */
 size_t msm_bases_size_bytes(const msm_bases* b);
 size_t msm_bases_num_points(const msm_bases* b);

@@ -186,6 +186,45 @@ def test_edge_cases(engine, oracle, ws, curve):
     assert_same_points(oracle, curve, got, want, "ragged")
 
 
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("c", [0, 11, 14])
+def test_window_table_path(engine, oracle, ws, curve, c):
+    """msm_bases_precompute: the folded window table gives the same group element as the plain
+    resident copy and as the oracle, including the edge cases; other call shapes on the same bases
+    keep working."""
+    n = 6000
+    pts, sc = adversarial_inputs(oracle, curve, n)
+    w = ws[curve]
+    bases_gpu = engine.upload_multiexp_bases(w, pts)
+    want = oracle.multiple_multiexp(curve, pts, sc, 1)
+    plain = engine.multiple_multiexp(w, bases_gpu, sc, 1, 8, True)
+    assert_same_points(oracle, curve, plain, want, "plain")
+    tc = bases_gpu.precompute(c)
+    assert tc >= 11 and (c == 0 or tc == c)
+    folded = engine.multiple_multiexp(w, bases_gpu, sc, 1, 8, True)
+    t = w.timings()
+    assert t["window_bits"] == tc
+    assert_same_points(oracle, curve, folded, want, "folded")
+    # a chunked call on the same handle takes the ordinary path
+    got = engine.multiple_multiexp(w, bases_gpu, sc, 8, 8, True)
+    assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc, 8), "chunked after precompute")
+
+
+def test_window_table_sharded_resident(engine, oracle):
+    """MultiexpKernel with resident sharded bases + tables (one device here; N devices in bench)."""
+    lib = engine.load_library()
+    n = 1 << 15
+    pts, sc = oracle.gen_points(0, SEED, n), oracle.gen_scalars(0, SEED, n)
+    kern = engine.MultiexpKernel.create([0], 0)
+    res = kern.upload_bases(pts)
+    assert lib.msm_bases_precompute(kern.workspace.handle, res, 0) == 0
+    got = kern.multiexp_resident(res, sc, 0)
+    assert_same_points(oracle, 0, got, oracle.multiexp_cpu(0, pts, sc), "resident + table")
+    part = kern.multiexp_resident(res, sc[:1000], 5)  # a sub-range falls back to the plain copy
+    assert_same_points(oracle, 0, part, oracle.multiexp_cpu(0, pts[5:], sc[:1000]), "sub-range")
+    lib.msm_bases_free(res)
+
+
 def test_bn254_batched_4096(engine, oracle, ws):
     """Shape of ag-cuda-ec/benches/multiexp.rs:19-22,56 scaled down: 64 MSMs of 2^12 points."""
     curve, chunks, cl = 0, 64, 4096

@@ -184,6 +184,20 @@ int main() {
     snprintf(nm, sizeof nm, "fmul_u29_bn254_%dw", bps * 4);
     run(nm, 2.0 * 136, 2000, bps, 128, sms, out, cyc, k_fmul<FieldU29<Bn254U29>>);
   }
+  // carry-save saturated product (fp_mul_cs): no IMAD.WIDE.U32.X at all
+  for (int bps = 1; bps <= 8; bps *= 2) {
+    char nm[64];
+    snprintf(nm, sizeof nm, "fmul_cs_bn254_%dw", bps * 4);
+    run(nm, 2.0 * 136, 2000, bps, 128, sms, out, cyc, k_fmul<FieldSat<Bn254Fq, true>>);
+  }
+  run("fmul_cs_bls381_8w", 2.0 * 300, 1000, 2, 128, sms, out, cyc, k_fmul<FieldSat<Bls381Fq, true>>);
+  run("fmul_cs_bls381_16w", 2.0 * 300, 1000, 4, 128, sms, out, cyc, k_fmul<FieldSat<Bls381Fq, true>>);
+  for (int bps = 1; bps <= 4; bps *= 2) {
+    char nm[64];
+    snprintf(nm, sizeof nm, "madd_cs_bn254_%dw", bps * 4);
+    run(nm, 2.0 * 1360, 300, bps, 128, sms, out, cyc, k_madd<FieldSat<Bn254Fq, true>>);
+  }
+  run("madd_cs_bls381_8w", 2.0 * 3000, 150, 2, 128, sms, out, cyc, k_madd<FieldSat<Bls381Fq, true>>);
   // mixed addition, counted at the algorithmic 10 products x 136 MAC
   for (int bps = 1; bps <= 4; bps *= 2) {
     char nm[64];

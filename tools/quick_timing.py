@@ -32,6 +32,11 @@ def main():
         bh = ctypes.c_void_p()
         assert lib.msm_bases_from_device(h, dp, n, ctypes.byref(bh)) == 0
         lib.msm_device_free(h, dp)
+        pre = int(os.environ.get("PRECOMPUTE", "-1"))
+        if pre >= 0:
+            t2 = time.time()
+            assert lib.msm_bases_precompute(h, bh, pre) == 0, lib.msm_last_error(h)
+            print("precompute: c=%d in %.3f s" % (lib.msm_bases_table_window(bh), time.time() - t2))
         for c in windows:
             ws.set_window_bits(c)
             best = None
