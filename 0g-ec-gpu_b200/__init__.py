@@ -36,3 +36,4 @@ from .multiexp import (  # noqa: F401
     upload_multiexp_bases_st,
 )
 from .kernel import MultiexpKernel, Worker  # noqa: F401
+from .sharding import chunk_size, shard_range  # noqa: F401

@@ -28,7 +28,7 @@ inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_task
     const double B = (double)(1u << (c - 1));
     const double bucket_bytes = (double)n_tasks_lines * W * B * (double)xyzz_bytes;
     if (bucket_bytes > 6e9) break;
-    const double cost = (double)W * ((double)chunk_len * 10.0 + B * (2.0 * 14.0 + 6.0));
+    const double cost = (double)W * ((double)chunk_len * 10.0 + B * 90.0);  // 90: measured cost of one bucket in the reduction, in field products
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -426,7 +426,7 @@ template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint
     for (uint32_t cc = 11; cc <= 24; cc++) {
       const uint32_t W = (bits + 1 + cc - 1) / cc;
       if ((uint64_t)W * sh.n >= (1ull << 31)) continue;
-      const double cost = (double)W * (double)sh.n * 10.0 + (double)(1u << (cc - 1)) * 34.0;
+      const double cost = (double)W * (double)sh.n * 10.0 + (double)(1u << (cc - 1)) * 90.0;
       if (cost < best) {
         best = cost;
         c = cc;

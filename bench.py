@@ -223,8 +223,8 @@ def main():
     assert lib.msm_set_stream(h, ctypes.c_void_p(stream.cuda_stream)) == 0
 
     n_total = 1 << args.log_n
-    n_local = n_total // world
-    start = rank * n_local
+    start, end = m.shard_range(n_total, world, rank)
+    n_local = end - start
     d_pts = torch.empty(n_local * 2 * fq, dtype=torch.uint8, device=dev)
     d_sc = torch.empty(n_local * 32, dtype=torch.uint8, device=dev)
     d_out = torch.zeros(3 * fq, dtype=torch.uint8, device=dev)

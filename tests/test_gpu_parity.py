@@ -292,3 +292,25 @@ def test_context_busy_and_errors(engine, oracle):
     kern2 = engine.MultiexpKernel.create_with_abort([0], lambda: True, 0)
     with pytest.raises(engine.EcErrorAborted):
         kern2.multiexp(engine.Worker(), pts, oracle.gen_scalars(0, 1, 64), 0)
+
+
+def test_multi_device_split_and_gather(engine, oracle):
+    """MultiexpKernel over every visible GPU: contiguous split ceil(n/devices)
+    (ec-gpu-proxy/src/multiexp.rs:329-337), partial points gathered on device 0 over peer copies
+    and summed there.  Needs >= 2 GPUs (gpurun --gpus 2); single-GPU boxes skip."""
+    lib = engine.load_library()
+    ndev = lib.msm_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = (1 << 16) + 123
+    for curve in CURVES:
+        pts, sc = oracle.gen_points(curve, SEED, n), oracle.gen_scalars(curve, SEED, n)
+        kern = engine.MultiexpKernel.create(list(range(ndev)), curve)
+        assert kern.num_kernels() == ndev
+        want = oracle.multiexp_cpu(curve, pts, sc)
+        assert_same_points(oracle, curve, kern.multiexp(engine.Worker(), pts, sc, 0), want, "host bases")
+        res = kern.upload_bases(pts)
+        assert_same_points(oracle, curve, kern.multiexp_resident(res, sc, 0), want, "resident shards")
+        assert lib.msm_bases_precompute(kern.workspace.handle, res, 0) == 0
+        assert_same_points(oracle, curve, kern.multiexp_resident(res, sc, 0), want, "resident shards + tables")
+        lib.msm_bases_free(res)
