@@ -87,7 +87,7 @@ template <class F> MSM_COLD Xyzz<F> xyzz_mdbl(const Affine<F>& a) {
   const E x3 = F::norm(F::template sub<3, 2>(F::sqr(m), F::add(s, s)));  // v<1.06+3
   const E d = F::template sub<5, 1>(s, x3);           // v<6.01 l<3
   r.x = x3;
-  r.y = F::norm(F::template sub<2, 1>(F::mul(m, d), F::mul(w, y)));      // (1,3),(1,1)  v<1.11+2
+  r.y = F::norm(F::mul_sub(m, d, w, y));                               // (1,3),(1,1)  v<1.11+2
   r.zz = v;
   r.zzz = w;
   return r;
@@ -107,7 +107,7 @@ template <class F> MSM_COLD Xyzz<F> xyzz_dbl(const Xyzz<F>& a) {
   const E x3 = F::norm(F::template sub<3, 2>(F::sqr(m), F::add(s, s)));  // v<1.11+3
   const E d = F::template sub<5, 1>(s, x3);           // v<6.1 l<3
   r.x = x3;
-  r.y = F::norm(F::template sub<2, 1>(F::mul(m, d), F::mul(w, a.y)));    // v<1.16+2
+  r.y = F::norm(F::mul_sub(m, d, w, a.y));                             // v<1.16+2
   r.zz = F::mul(v, a.zz);
   r.zzz = F::mul(w, a.zzz);
   return r;
@@ -142,7 +142,7 @@ template <class F> MSM_HD void xyzz_madd(Xyzz<F>& acc, const Affine<F>& b) {
   const E s = F::add(F::add(ppp, q), q);              // v<3.26 l<3
   const E x3 = F::norm(F::template sub<5, 3>(F::sqr(r), s));  // v<1.22+5
   const E d = F::template sub<7, 1>(q, x3);           // v<8.08 l<3
-  const E y3 = F::norm(F::template sub<2, 1>(F::mul(r, d), F::mul(acc.y, ppp)));  // (1,3),(1,1)  v<1.29+2
+  const E y3 = F::norm(F::mul_sub(r, d, acc.y, ppp));  // r*d - Y1*PPP, one reduction; (1,3),(1,1)  v<1.29+2
   acc.x = x3;
   acc.y = y3;
   acc.zz = F::mul(acc.zz, pp);                        // v<1.08
@@ -171,7 +171,7 @@ template <class F> MSM_COLD Xyzz<F> xyzz_add(const Xyzz<F>& a, const Xyzz<F>& b)
   Xyzz<F> o;
   o.x = F::norm(F::template sub<5, 3>(F::sqr(r), s)); // v<1.07+5
   const E d = F::template sub<7, 1>(q, o.x);          // v<8.1 l<3
-  o.y = F::norm(F::template sub<2, 1>(F::mul(r, d), F::mul(s1, ppp)));  // v<1.16+2
+  o.y = F::norm(F::mul_sub(r, d, s1, ppp));                           // v<1.16+2
   o.zz = F::mul(F::mul(a.zz, b.zz), pp);
   o.zzz = F::mul(F::mul(a.zzz, b.zzz), ppp);
   return o;

@@ -45,12 +45,15 @@ ScalarField scalar_field(int curve) {
 }
 
 const FieldOps* pick_ops(int curve) {
-  if (curve == MSM_CURVE_BLS12_381_G1) return field_ops_bls381_sat();
-  // BN254: saturated 32-bit limbs (carry-chained IMAD.WIDE.U32.X) measured faster on B200 than the
-  // carry-free 29-bit build (profiles/r01_imad_peak_v2.json); MSM_B200_FIELD=u29 selects the latter.
+  // Default: saturated 32-bit limbs with values kept in [0, 2p) ("sat32-lazy").  MSM_B200_FIELD
+  // selects the alternatives that were built and measured:
+  //   sat32  canonical values, conditional subtraction after every product
+  //   u29    BN254 only: nine 29-bit limbs, carry-free IMAD.WIDE (slower on B200)
   const char* env = getenv("MSM_B200_FIELD");
+  const bool want_sat = env && (strcmp(env, "sat32") == 0 || strcmp(env, "sat") == 0);
+  if (curve == MSM_CURVE_BLS12_381_G1) return want_sat ? field_ops_bls381_sat() : field_ops_bls381_lazy();
   if (env && strcmp(env, "u29") == 0) return field_ops_bn254_u29();
-  return field_ops_bn254_sat();
+  return want_sat ? field_ops_bn254_sat() : field_ops_bn254_lazy();
 }
 
 #define LOCK_OR_BUSY(ctx)            \

@@ -133,5 +133,7 @@ struct FieldOps {
 const FieldOps* field_ops_bn254_u29();
 const FieldOps* field_ops_bn254_sat();
 const FieldOps* field_ops_bls381_sat();
+const FieldOps* field_ops_bn254_lazy();
+const FieldOps* field_ops_bls381_lazy();
 
 }  // namespace msm

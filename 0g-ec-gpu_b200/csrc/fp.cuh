@@ -103,6 +103,22 @@ template <class P> MSM_HD void fp_csub_p(uint32_t* r) {
   for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
 }
 
+// limb i of K*p (K = 1 or 2), compile-time
+template <class P, int K> MSM_HD constexpr uint32_t fp_kp(int i) {
+  return K == 1 ? P::P(i) : (uint32_t)((P::P(i) << 1) | (i ? (P::P(i - 1) >> 31) : 0u));
+}
+// r = (r >= K p) ? r - K p : r
+template <class P, int K> MSM_HD void fp_csub_kp(uint32_t* r) {
+  constexpr int N = P::N;
+  uint32_t t[N];
+  t[0] = sub_cc(r[0], fp_kp<P, K>(0));
+#pragma unroll
+  for (int i = 1; i < N; i++) t[i] = subc_cc(r[i], fp_kp<P, K>(i));
+  uint32_t borrow = subc(0u, 0u);
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
+}
+
 template <class P> MSM_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
   constexpr int N = P::N;
   Fp<P> r;
@@ -188,7 +204,8 @@ MSM_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
   O[N - 1] = addc(O[N - 1], 0u);
 }
 
-template <class P> MSM_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+// a*b/R without the final conditional subtraction: result < a*b/R + p (< 2p for a, b < 2p)
+template <class P> MSM_HD Fp<P> fp_mul_nored(const Fp<P>& a, const Fp<P>& b) {
   constexpr int N = P::N;
   static_assert(N % 2 == 0, "even limb count required");
   uint32_t X[N], Y[N];
@@ -204,7 +221,68 @@ template <class P> MSM_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #pragma unroll
   for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
   r.v[N - 1] = addc(X[N - 1], 0u);
+  return r;
+}
+template <class P> MSM_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r = fp_mul_nored<P>(a, b);
   fp_csub_p<P>(r.v);
+  return r;
+}
+
+// (a*b + c*d)/R with ONE Montgomery reduction: each row adds a*b[i] and c*d[i] before the
+// quotient digit is taken.  Saves N^2+N of the 4N^2+2N multiplies of two separate products.
+// Bound: T < 5 p 2^32 + 2p < 2^(32(N+1)) for a, b, c, d < 2p (p < 0.19 * 2^(32N)), so the carry
+// structure of mont_row is unchanged.  Result < (ab + cd)/R + p, not reduced.
+template <class P, bool FIRST>
+MSM_HD void mont_row2(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, const uint32_t* c, uint32_t di) {
+  constexpr int N = P::N;
+  if (FIRST) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      mul_wide(E[j], E[j + 1], a[j], bi);
+      mul_wide(O[j], O[j + 1], a[j + 1], bi);
+    }
+  } else {
+    E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) madc_wide_cc3(O[j], O[j + 1], a[j + 1], bi, O[j + 2], O[j + 3]);
+    madc_wide_0(O[N - 2], O[N - 1], a[N - 1], bi);
+    mad_wide_cc(E[0], E[1], a[0], bi);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], a[j], bi);
+    O[N - 1] = addc(O[N - 1], 0u);
+  }
+  // second product of the row
+  mad_wide_cc(O[0], O[1], c[1], di);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(O[j], O[j + 1], c[j + 1], di);
+  mad_wide_cc(E[0], E[1], c[0], di);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], c[j], di);
+  O[N - 1] = addc(O[N - 1], 0u);
+  const uint32_t m = mul_lo(E[0], P::INV);
+  mad_wide_cc(O[0], O[1], P::P(1), m);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(O[j], O[j + 1], P::P(j + 1), m);
+  mad_wide_cc(E[0], E[1], P::P(0), m);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], P::P(j), m);
+  O[N - 1] = addc(O[N - 1], 0u);
+}
+template <class P> MSM_HD Fp<P> fp_mul2_nored(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+  constexpr int N = P::N;
+  uint32_t X[N], Y[N];
+  mont_row2<P, true>(X, Y, a.v, b.v[0], c.v, d.v[0]);
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    mont_row2<P, false>(Y, X, a.v, b.v[i], c.v, d.v[i]);
+    if (i + 1 < N) mont_row2<P, false>(X, Y, a.v, b.v[i + 1], c.v, d.v[i + 1]);
+  }
+  Fp<P> r;
+  r.v[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
+  r.v[N - 1] = addc(X[N - 1], 0u);
   return r;
 }
 
@@ -351,6 +429,12 @@ template <class P, bool CS = false> struct FieldSat {
   template <int LO, int HI> static MSM_HD bool is_multiple_of_p(const Elem& a) { return fp_is_zero<P>(a); }
   static MSM_HD Elem mul(const Elem& a, const Elem& b) { return CS ? fp_mul_cs<P>(a, b) : fp_mul<P>(a, b); }
   static MSM_HD Elem sqr(const Elem& a) { return mul(a, a); }
+  // a*b - c*d with one reduction: (a*b + (p - c)*d)/R < 2p^2/R + p < 2p
+  static MSM_HD Elem mul_sub(const Elem& a, const Elem& b, const Elem& c, const Elem& d) {
+    Elem r = fp_mul2_nored<P>(a, b, fp_neg<P>(c), d);
+    fp_csub_p<P>(r.v);
+    return r;
+  }
   static MSM_HD Elem inv(const Elem& a) { return fp_inv<P>(a); }
 
   // resident-base coordinate <-> registers (same layout as the API: nothing to do)
@@ -376,6 +460,105 @@ template <class P, bool CS = false> struct FieldSat {
   // canonical integer (non-Montgomery) in API word layout
   static MSM_HD void to_canonical_words(const Elem& a, uint32_t* w) {
     Elem c = fp_from_mont<P>(a);
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i] = c.v[i];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FieldSatLazy<P>: the same 32-bit-limb arithmetic with values kept in [0, 2p) instead of [0, p).
+// A Montgomery product of two values < 2p is < 4p^2/R + p < 2p (p < 0.19 R for both curves), so the
+// conditional subtraction after every product -- 17 of the ~190 instructions, none of which
+// overlaps with the multiplier pipe on B200 -- disappears.  add/sub fold back into [0, 2p).
+// Zero tests compare against 0 and p; the infinity flag is still "all limbs zero" because a finite
+// point's ZZ is a product of non-zero residues and is never 0 or p.
+// ---------------------------------------------------------------------------------------------
+template <class P> struct FieldSatLazy {
+  static constexpr int N = P::N;
+  static constexpr int API_WORDS = P::N;
+  static constexpr int PACKED_WORDS = P::N;
+  using Elem = Fp<P>;
+
+  static MSM_HD Elem zero() { return fp_zero<P>(); }
+  static MSM_HD Elem one() { return fp_one<P>(); }
+  static MSM_HD bool is_zero_limbs(const Elem& a) { return fp_is_zero<P>(a); }
+  static MSM_HD Elem add(const Elem& a, const Elem& b) {
+    Elem r;
+    r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+    r.v[N - 1] = addc(a.v[N - 1], b.v[N - 1]);  // 4p < 2^(32N)
+    fp_csub_kp<P, 2>(r.v);
+    return r;
+  }
+  template <int K, int LM> static MSM_HD Elem sub(const Elem& a, const Elem& b) {
+    Elem r;
+    r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+    const uint32_t mask = subc(0u, 0u);
+    r.v[0] = add_cc(r.v[0], fp_kp<P, 2>(0) & mask);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(r.v[i], fp_kp<P, 2>(i) & mask);
+    r.v[N - 1] = addc(r.v[N - 1], fp_kp<P, 2>(N - 1) & mask);
+    return r;
+  }
+  template <int K, int LM> static MSM_HD Elem neg(const Elem& a) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) nz |= a.v[i];
+    const uint32_t mask = nz ? 0xffffffffu : 0u;
+    Elem r;
+    r.v[0] = sub_cc(fp_kp<P, 2>(0) & mask, a.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = subc_cc(fp_kp<P, 2>(i) & mask, a.v[i]);
+    r.v[N - 1] = subc(fp_kp<P, 2>(N - 1) & mask, a.v[N - 1]);
+    return r;
+  }
+  static MSM_HD Elem norm(const Elem& a) { return a; }
+  template <int LO, int HI> static MSM_HD bool is_multiple_of_p(const Elem& a) {
+    uint32_t z = 0, e = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      z |= a.v[i];
+      e |= a.v[i] ^ P::P(i);
+    }
+    return z == 0 || e == 0;
+  }
+  static MSM_HD Elem mul(const Elem& a, const Elem& b) { return fp_mul_nored<P>(a, b); }
+  static MSM_HD Elem sqr(const Elem& a) { return fp_mul_nored<P>(a, a); }
+  // a*b - c*d: (a*b + (2p - c)*d)/R < 8p^2/R + p < 4p -> one fold back below 2p
+  static MSM_HD Elem mul_sub(const Elem& a, const Elem& b, const Elem& c, const Elem& d) {
+    Elem r = fp_mul2_nored<P>(a, b, neg<2, 1>(c), d);
+    fp_csub_kp<P, 2>(r.v);
+    return r;
+  }
+  static MSM_HD Elem canonical(const Elem& a) {
+    Elem r = a;
+    fp_csub_p<P>(r.v);
+    return r;
+  }
+  static MSM_COLD Elem inv(const Elem& a) { return fp_inv<P>(canonical(a)); }
+
+  static MSM_HD Elem unpack(const uint32_t* w) {
+    Elem r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = w[i];
+    return r;
+  }
+  static MSM_HD void api_to_packed(const uint32_t* api, uint32_t* packed) {
+#pragma unroll
+    for (int i = 0; i < N; i++) packed[i] = api[i];
+  }
+  static MSM_HD void to_packed(const Elem& a, uint32_t* packed) { to_api(a, packed); }
+  static MSM_HD Elem from_api(const uint32_t* w) { return unpack(w); }
+  static MSM_HD void to_api(const Elem& a, uint32_t* w) {
+    const Elem c = canonical(a);
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i] = c.v[i];
+  }
+  static MSM_HD void to_canonical_words(const Elem& a, uint32_t* w) {
+    Elem c = fp_from_mont<P>(canonical(a));
 #pragma unroll
     for (int i = 0; i < N; i++) w[i] = c.v[i];
   }

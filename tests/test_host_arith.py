@@ -5,6 +5,7 @@ same formulas run here against the oracle, for both field implementations:
   impl 0  FieldSat  saturated 32-bit limbs (BN254, BLS12-381)
   impl 1  FieldU29  lazy 29-bit limbs (BN254) -- built with MSM_CHECK_BOUNDS, which aborts the
           process on any 64-bit column overflow or negative limb in the lazy-reduction scheme.
+  impl 2  FieldSatLazy  saturated 32-bit limbs with values in [0, 2p) (the engine's default)
 """
 import ctypes
 import os
@@ -16,7 +17,7 @@ import pytest
 from util import FQ, assert_same_points
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-IMPLS = [(0, 0), (0, 1), (1, 0)]  # (curve, impl)
+IMPLS = [(0, 0), (0, 1), (1, 0), (0, 2), (1, 2)]  # (curve, impl); impl 2 = FieldSatLazy, values in [0, 2p)
 
 
 @pytest.fixture(scope="module")
@@ -37,7 +38,7 @@ def _rand_fq(oracle, curve, n, rng):
     fb = FQ[curve]
     vals = [int.from_bytes(rng.bytes(fb + 8), "little") % p for _ in range(n)]
     # extremes: 0, 1, p-1, all-ones limb patterns below p
-    vals[:6] = [0, 1, p - 1, p - 2, (1 << (8 * fb - 3)) - 1, (p >> 1)]
+    vals[:6] = [0, 1, p - 1, p - 2, (1 << (p.bit_length() - 1)) - 1, (p >> 1)]
     return np.frombuffer(b"".join(v.to_bytes(fb, "little") for v in vals), dtype=np.uint8).copy()
 
 

@@ -198,6 +198,13 @@ int main() {
     run(nm, 2.0 * 1360, 300, bps, 128, sms, out, cyc, k_madd<FieldSat<Bn254Fq, true>>);
   }
   run("madd_cs_bls381_8w", 2.0 * 3000, 150, 2, 128, sms, out, cyc, k_madd<FieldSat<Bls381Fq, true>>);
+  // values in [0, 2p), no conditional subtraction after products, fused r*d - y*ppp
+  for (int bps = 1; bps <= 4; bps *= 2) {
+    char nm[64];
+    snprintf(nm, sizeof nm, "madd_lazy_bn254_%dw", bps * 4);
+    run(nm, 2.0 * 1360, 300, bps, 128, sms, out, cyc, k_madd<FieldSatLazy<Bn254Fq>>);
+  }
+  run("madd_lazy_bls381_8w", 2.0 * 3000, 150, 2, 128, sms, out, cyc, k_madd<FieldSatLazy<Bls381Fq>>);
   // mixed addition, counted at the algorithmic 10 products x 136 MAC
   for (int bps = 1; bps <= 4; bps *= 2) {
     char nm[64];
