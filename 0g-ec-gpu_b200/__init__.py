@@ -29,6 +29,7 @@ from .multiexp import (  # noqa: F401
     init_global_workspace,
     init_local_workspace,
     multiple_multiexp,
+    multiple_multiexp_montgomery,
     multiple_multiexp_mt,
     multiple_multiexp_st,
     upload_multiexp_bases,

@@ -124,6 +124,8 @@ def load_library() -> ctypes.CDLL:
         "msm_multiple_multiexp_device_timed": ([vp, vp, vp, sz, u32, vp, u32, ctypes.POINTER(ctypes.c_float),
                                                 ctypes.POINTER(ctypes.c_float)], i32),
         "msm_set_stream": ([vp, vp], i32),
+        "msm_scalars_from_montgomery_device": ([vp, vp, sz, vp], i32),
+        "msm_multiple_multiexp_montgomery": ([vp, vp, vp, sz, u32, vp], i32),
         "msm_multiexp": ([vp, vp, vp, sz, vp], i32),
         "msm_multiexp_resident": ([vp, vp, sz, vp, sz, vp], i32),
         "msm_sum_points_device": ([vp, vp, sz, vp], i32),

@@ -324,6 +324,54 @@ int msm_synth_scalars_device(msm_ctx* ctx, uint64_t seed, size_t start, size_t n
   return MSM_OK;
 }
 
+int msm_scalars_from_montgomery_device(msm_ctx* ctx, const void* d_in, size_t n, void* d_out) {
+  if (!ctx || (n && (!d_in || !d_out))) return MSM_ERR_INVALID;
+  if (n == 0) return MSM_OK;
+  if (n >= (1ull << 32)) return MSM_ERR_TOO_LARGE;
+  LOCK_OR_BUSY(ctx);
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const uint32_t grid = (uint32_t)((n + 255) / 256);
+  if (ctx->curve == MSM_CURVE_BN254_G1)
+    k_scalars_unmont<Bn254Fr><<<grid, 256, 0, dc.stream>>>(static_cast<const uint32_t*>(d_in), (uint32_t)n, static_cast<uint32_t*>(d_out));
+  else
+    k_scalars_unmont<Bls381Fr><<<grid, 256, 0, dc.stream>>>(static_cast<const uint32_t*>(d_in), (uint32_t)n, static_cast<uint32_t*>(d_out));
+  dc.launches += 1;
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  return MSM_OK;
+}
+
+int msm_multiple_multiexp_montgomery(msm_ctx* ctx, const msm_bases* bases, const void* scalars_mont, size_t L,
+                                     uint32_t num_chunks, void* out) {
+  if (!ctx || !bases || !scalars_mont || !out || bases->ctx != ctx || L == 0 || L >= (1ull << 31)) return MSM_ERR_INVALID;
+  void* d_sc = nullptr;
+  size_t n_tasks = 0;
+  {
+    LOCK_OR_BUSY(ctx);
+    DeviceCtx& dc = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(dc.dev));
+    CU_TRY(ctx, cudaMalloc(&d_sc, L * 32));
+    cudaError_t e = cudaMemcpyAsync(d_sc, scalars_mont, L * 32, cudaMemcpyHostToDevice, dc.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dc.stream);
+    if (e != cudaSuccess) {
+      cudaFree(d_sc);
+      set_error(ctx, std::string("msm_multiple_multiexp_montgomery: ") + cudaGetErrorString(e));
+      return MSM_ERR_CUDA;
+    }
+    n_tasks = (bases->n / L) * num_chunks;
+  }
+  int rc = msm_scalars_from_montgomery_device(ctx, d_sc, L, d_sc);
+  void* d_out = nullptr;
+  const size_t out_bytes = n_tasks * (ctx->ops->api_point_bytes / 2) * 3;
+  if (rc == MSM_OK && cudaMalloc(&d_out, out_bytes ? out_bytes : 1) != cudaSuccess) rc = MSM_ERR_CUDA;
+  if (rc == MSM_OK) rc = msm_multiple_multiexp_device(ctx, bases, d_sc, L, num_chunks, d_out);
+  if (rc == MSM_OK && cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = MSM_ERR_CUDA;
+  cudaFree(d_sc);
+  if (d_out) cudaFree(d_out);
+  return rc;
+}
+
 int msm_test_fq_op(msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
   if (!ctx || !a || !out || op < 0 || op > 8) return MSM_ERR_INVALID;
   if (count == 0) return MSM_OK;

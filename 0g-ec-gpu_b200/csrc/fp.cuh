@@ -60,6 +60,47 @@ struct Bls381Fq {
   static constexpr uint32_t CURVE_B = 4;  // y^2 = x^3 + 4
 };
 
+// Scalar fields Fr (only Montgomery -> canonical conversion of exponents runs on them:
+// PrimeFieldRepr::to_bigint, ag-types/src/impls.rs:7-18, moved onto the device).
+struct Bn254Fr {
+  static constexpr int N = 8;
+  static constexpr uint32_t INV = 0xefffffffu;
+  static MSM_HD constexpr uint32_t P(int i) {
+    constexpr uint32_t t[N] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return t[i];
+  }
+  static MSM_HD constexpr uint32_t ONE(int i) {
+    constexpr uint32_t t[N] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return t[i];
+  }
+  static MSM_HD constexpr uint32_t R2(int i) {
+    constexpr uint32_t t[N] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                               0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return t[i];
+  }
+};
+struct Bls381Fr {  // 255-bit modulus: p < 2^(32N-1) still satisfies the bound of mont_row
+  static constexpr int N = 8;
+  static constexpr uint32_t INV = 0xffffffffu;
+  static MSM_HD constexpr uint32_t P(int i) {
+    constexpr uint32_t t[N] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                               0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    return t[i];
+  }
+  static MSM_HD constexpr uint32_t ONE(int i) {
+    constexpr uint32_t t[N] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                               0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+    return t[i];
+  }
+  static MSM_HD constexpr uint32_t R2(int i) {
+    constexpr uint32_t t[N] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                               0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+    return t[i];
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 template <class P> struct Fp {
   static constexpr int N = P::N;

@@ -590,6 +590,24 @@ __global__ void k_test_ec(int op, const ApiJacobian<F>* __restrict__ a, const vo
   xyzz_to_api_jacobian<F>(r, &o[i]);
 }
 
+// Exponents handed over in Montgomery form (arkworks' in-memory Fr) -> canonical integers, the
+// device-side replacement of the host pass PrimeFieldRepr::to_bigint (ag-types/src/impls.rs:7-18,
+// "10ms for 1M" in ag-cuda-ec/benches/multiexp.rs:28-36).  In place is allowed.
+template <class PR>
+__global__ void k_scalars_unmont(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp<PR> a;
+  uint32_t k[8];
+  load_scalar(in, i, k);
+#pragma unroll
+  for (int j = 0; j < 8; j++) a.v[j] = k[j];
+  const Fp<PR> c = fp_from_mont<PR>(a);
+  uint4* o = reinterpret_cast<uint4*>(out) + 2 * (size_t)i;
+  o[0] = make_uint4(c.v[0], c.v[1], c.v[2], c.v[3]);
+  o[1] = make_uint4(c.v[4], c.v[5], c.v[6], c.v[7]);
+}
+
 // --- synthetic inputs -------------------------------------------------------------------------
 MSM_HD uint64_t splitmix64(uint64_t seed, uint64_t idx) {
   uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;

@@ -153,6 +153,20 @@ def multiple_multiexp(workspace: Workspace, bases_gpu: DeviceData, exponents, nu
     return out
 
 
+def multiple_multiexp_montgomery(workspace: Workspace, bases_gpu: DeviceData, exponents_mont, num_chunks: int) -> np.ndarray:
+    """Engine extension: `exponents_mont` are Fr elements still in
+    Montgomery form ([L, 32] uint8, arkworks' in-memory layout); the conversion that
+    PrimeFieldRepr::to_bigint does on the host runs on the device instead."""
+    e = _as_u8(exponents_mont, 32, "exponents")
+    L = e.size // 32
+    num_lines = bases_gpu.num_points() // L
+    out = np.zeros((num_lines * num_chunks, 3 * fq_bytes(workspace.curve)), dtype=np.uint8)
+    rc = load_library().msm_multiple_multiexp_montgomery(workspace.handle, bases_gpu._h, e.ctypes.data, L, num_chunks,
+                                                         out.ctypes.data)
+    check(rc, workspace.handle, cuda_style=True)
+    return out
+
+
 # #[auto_workspace] (ag-cuda-workspace-macro/src/lib.rs:8-55): f_st uses GLOBAL, f_mt uses LOCAL
 def upload_multiexp_bases_st(bases, curve: int | None = None) -> DeviceData:
     return upload_multiexp_bases(init_global_workspace(curve), bases)

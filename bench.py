@@ -205,6 +205,12 @@ def main():
                   % (args.gpus, world, args.gpus), file=sys.stderr)
         sys.exit(2)
 
+    # stdout carries exactly one JSON line: anything libraries print there while we run (NCCL's
+    # version banner, for one) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -355,7 +361,8 @@ def main():
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(curve, min(args.cpu_log_sample, args.log_n))
             out["spot_check_vs_oracle"] = spot_check(m, curve, local_rank)
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -135,6 +135,15 @@ int msm_multiple_multiexp(msm_ctx* ctx, const msm_bases* bases, const void* scal
 int msm_multiple_multiexp_device(msm_ctx* ctx, const msm_bases* bases, const void* d_scalars,
                                  size_t L, uint32_t num_chunks, void* d_out_jacobian);
 
+/* Exponents in Montgomery form (arkworks' in-memory Fr, 4 x u64 little-endian) -> canonical
+ * integers on the device: replaces the host pass PrimeFieldRepr::to_bigint
+ * (ag-types/src/impls.rs:7-18) that the reference's benches time separately
+ * (ag-cuda-ec/benches/multiexp.rs:28-36).  d_in == d_out is allowed. */
+int msm_scalars_from_montgomery_device(msm_ctx* ctx, const void* d_scalars_mont, size_t n, void* d_scalars_out);
+/* msm_multiple_multiexp for a host row of exponents still in Montgomery form. */
+int msm_multiple_multiexp_montgomery(msm_ctx* ctx, const msm_bases* bases, const void* scalars_mont, size_t L,
+                                     uint32_t num_chunks, void* out_jacobian);
+
 /* The same call repeated `repeats` times back to back with CUDA events recorded on the launching
  * stream around the whole sequence (total_ms) and around every bucket-accumulation kernel (their
  * sum in accumulate_ms).  Measurement aid for bench.py; results as above. */

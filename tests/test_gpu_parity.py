@@ -225,6 +225,24 @@ def test_window_table_sharded_resident(engine, oracle):
     lib.msm_bases_free(res)
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_montgomery_scalars_on_device(engine, oracle, pyref, ws, curve):
+    """exponents handed over in Montgomery form are converted on the
+    device (FIELD_unmont, ag-build/cl/field.cl:365-377) and give the same MSM."""
+    cv = pyref.CURVES[curve]
+    n = 2048
+    pts, sc = adversarial_inputs(oracle, curve, n)
+    R = 1 << 256
+    mont = np.zeros_like(sc)
+    for i in range(n):
+        k = int.from_bytes(sc[i].tobytes(), "little")
+        mont[i] = np.frombuffer((k * R % cv.r).to_bytes(32, "little"), dtype=np.uint8)
+    bases_gpu = engine.upload_multiexp_bases(ws[curve], pts)
+    got = engine.multiple_multiexp_montgomery(ws[curve], bases_gpu, mont, 4)
+    want = oracle.multiple_multiexp(curve, pts, sc, 4)
+    assert_same_points(oracle, curve, got, want, "montgomery scalars")
+
+
 def test_bn254_batched_4096(engine, oracle, ws):
     """Shape of ag-cuda-ec/benches/multiexp.rs:19-22,56 scaled down: 64 MSMs of 2^12 points."""
     curve, chunks, cl = 0, 64, 4096

@@ -19,15 +19,18 @@ def main():
     h = ws.handle
     print("field impl:", lib.msm_field_impl(h).decode())
     fq = m.fq_bytes(curve)
+    chunks = int(os.environ.get("CHUNKS", "1"))   # tasks per line (ag_cuda_ec::multiple_multiexp num_chunks)
+    lines = int(os.environ.get("LINES", "1"))     # base lines sharing the scalar row (AMT shape)
     for lg in sizes:
-        n = 1 << lg
+        L = 1 << lg
+        n = L * lines
         dp, ds, do = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         assert lib.msm_device_alloc(h, n * 2 * fq, ctypes.byref(dp)) == 0
-        assert lib.msm_device_alloc(h, n * 32, ctypes.byref(ds)) == 0
-        assert lib.msm_device_alloc(h, 3 * fq, ctypes.byref(do)) == 0
+        assert lib.msm_device_alloc(h, L * 32, ctypes.byref(ds)) == 0
+        assert lib.msm_device_alloc(h, 3 * fq * chunks * lines, ctypes.byref(do)) == 0
         t0 = time.time()
         assert lib.msm_synth_points_device(h, 0x0BADC0DE, 0, n, dp) == 0
-        assert lib.msm_synth_scalars_device(h, 0x0BADC0DE, 0, n, ds) == 0
+        assert lib.msm_synth_scalars_device(h, 0x0BADC0DE, 0, L, ds) == 0
         t1 = time.time()
         bh = ctypes.c_void_p()
         assert lib.msm_bases_from_device(h, dp, n, ctypes.byref(bh)) == 0
@@ -41,16 +44,17 @@ def main():
             ws.set_window_bits(c)
             best = None
             for it in range(4):
-                rc = lib.msm_multiple_multiexp_device(h, bh, ds, n, 1, do)
+                rc = lib.msm_multiple_multiexp_device(h, bh, ds, L, chunks, do)
                 assert rc == 0, (rc, lib.msm_last_error(h))
                 t = ws.timings()
                 if it > 0 and (best is None or t["total_ms"] < best["total_ms"]):
                     best = t
             pts = n / (best["total_ms"] * 1e-3)
-            print(json.dumps({"log_n": lg, "c": best["window_bits"], "W": best["num_windows"],
+            macs = {0: 21760, 1: 48000}[curve]
+            print(json.dumps({"log_L": lg, "lines": lines, "chunks": chunks, "log_n": lg, "c": best["window_bits"], "W": best["num_windows"],
                               "total_ms": round(best["total_ms"], 3), "sort_ms": round(best["sort_ms"], 3),
                               "acc_ms": round(best["accumulate_ms"], 3), "red_ms": round(best["reduce_ms"], 3),
-                              "points_per_s": round(pts), "imad_roofline_frac": round(pts * 21760 / 1.8612e13, 4),
+                              "points_per_s": round(pts), "imad_roofline_frac": round(pts * macs / 1.8612e13, 4),
                               "synth_s": round(t1 - t0, 2)}))
         ws.set_window_bits(0)
         lib.msm_bases_free(bh)
