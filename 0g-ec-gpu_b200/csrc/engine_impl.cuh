@@ -28,7 +28,11 @@ inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_task
     const double B = (double)(1u << (c - 1));
     const double bucket_bytes = (double)n_tasks_lines * W * B * (double)xyzz_bytes;
     if (bucket_bytes > 6e9) break;
-    const double cost = (double)W * ((double)chunk_len * 10.0 + B * 90.0);  // 90: measured cost of one bucket in the reduction, in field products
+    // cost of one bucket in the reduction, in field products (measured): with very many (task,
+    // window) groups one thread owns a whole group and pays the two additions of the running sum;
+    // with few groups the per-thread fix-up, the shared-memory tree and low occupancy triple that
+    const double per_bucket = (double)n_tasks_lines * W >= 32768.0 ? 34.0 : 90.0;
+    const double cost = (double)W * ((double)chunk_len * 10.0 + B * per_bucket);
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -186,8 +190,12 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
       std::swap(src, dst);
       pg = out_pg;
     }
-    const uint32_t wt = Ws < 32 ? 32 : (Ws > 256 ? 256 : ((Ws + 31) / 32) * 32);
-    k_window_combine<F><<<pl.n_tasks, wt, (size_t)Ws * sizeof(Xyzz<F>), st>>>(src, Ws, pg, g.c, d_out);
+    if (pl.n_tasks >= 512) {
+      k_window_combine_batched<F><<<(pl.n_tasks + tb - 1) / tb, tb, 0, st>>>(src, pl.n_tasks, Ws, pg, g.c, d_out);
+    } else {
+      const uint32_t wt = Ws < 32 ? 32 : (Ws > 256 ? 256 : ((Ws + 31) / 32) * 32);
+      k_window_combine<F><<<pl.n_tasks, wt, (size_t)Ws * sizeof(Xyzz<F>), st>>>(src, Ws, pg, g.c, d_out);
+    }
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[4], st));
   dc.launches += 10;

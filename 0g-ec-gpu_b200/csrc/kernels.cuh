@@ -454,6 +454,24 @@ __global__ void k_window_combine(const Xyzz<F>* __restrict__ group_partials, uin
   }
 }
 
+// Many small tasks (batched per-segment commitments, the AMT shape): one THREAD per task does the
+// same fold, so a warp finishes 32 tasks in the time the block-per-task form finishes one.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_window_combine_batched(const Xyzz<F>* __restrict__ group_partials, uint32_t n_tasks, uint32_t W, uint32_t PG,
+                         uint32_t c, ApiJacobian<F>* __restrict__ out) {
+  const uint32_t task = blockIdx.x * blockDim.x + threadIdx.x;
+  if (task >= n_tasks) return;
+  Xyzz<F> acc = xyzz_inf<F>();
+  for (int w = (int)W - 1; w >= 0; w--) {
+    if (w != (int)W - 1)
+      for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl<F>(acc);
+    const Xyzz<F>* src = group_partials + ((size_t)task * W + w) * PG;
+    for (uint32_t k = 0; k < PG; k++) acc = xyzz_add<F>(acc, load_vec(src + k));
+  }
+  xyzz_to_api_jacobian<F>(acc, &out[task]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Boundary and helper kernels: resident-copy conversion, sum of Jacobian points, Jacobian ->
 // affine, per-primitive test kernels (counterpart of ag-build/cl/test.cl), synthetic inputs.

@@ -253,6 +253,19 @@ def test_bn254_batched_4096(engine, oracle, ws):
     assert_same_points(oracle, curve, got, want, "64 x 4096")
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_many_small_tasks(engine, oracle, ws, curve):
+    """2 lines x 1024 chunks x 16 points: the thread-per-task window combine (n_tasks >= 512)."""
+    chunks, cl, lines = 1024, 16, 2
+    pts, sc = _synth(engine, ws[curve], curve, chunks * cl * lines)
+    sc = sc[: chunks * cl]
+    bases_gpu = engine.upload_multiexp_bases(ws[curve], pts)
+    got = engine.multiple_multiexp(ws[curve], bases_gpu, sc, chunks, 8, True)
+    want = oracle.multiple_multiexp(curve, pts, sc, chunks)
+    assert got.shape[0] == lines * chunks
+    assert_same_points(oracle, curve, got, want, "2 x 1024 x 16")
+
+
 def test_bn254_2pow20_bit_exact(engine, oracle, ws):
     """BASELINE.json configs[1]: BN254 G1 MSM 2^20 on one B200, bit-exact vs the CPU multiexp."""
     curve, n = 0, 1 << 20
