@@ -60,6 +60,8 @@ class Timings(ctypes.Structure):
         ("num_windows", ctypes.c_uint32),
         ("num_entries", ctypes.c_uint64),
         ("kernel_launches", ctypes.c_uint64),
+        ("scatter_passes", ctypes.c_uint32),
+        ("sub_batches", ctypes.c_uint32),
     ]
 
     def as_dict(self):

@@ -60,6 +60,8 @@ struct DeviceCtx {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   void* small = nullptr;  // 64 KiB persistent (partial-point gather)
+  cudaStream_t copy_stream = nullptr;  // host->device scalar chunks of pipelined calls
+  cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct FieldOps;

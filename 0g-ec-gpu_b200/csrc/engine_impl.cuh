@@ -45,17 +45,23 @@ struct Plan {
   Geometry geo;
   uint32_t n_lines, S, n_slices, Q, RW, PG, n_tasks;
   uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
+  uint32_t n_sub;   // sub-batches of a pipelined single-task call (each fills its own bucket array)
+  mutable uint32_t scatter_passes = 1;  // filled in by enqueue_msm
   uint64_t E_max;
   size_t scratch_bytes;
 };
 
 // table_c != 0: the bases are a window table built for window size table_c covering exactly L points
 template <class F>
-int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, Plan& pl, uint32_t table_c = 0) {
+int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, Plan& pl, uint32_t table_c = 0,
+              uint32_t n_sub = 1) {
   if (L == 0 || num_chunks == 0 || n_lines == 0 || num_chunks > L) return MSM_ERR_INVALID;
   Geometry& g = pl.geo;
   g.fold = table_c ? 1 : 0;
   g.table_stride = L;
+  g.point_offset = 0;
+  if (n_lines != 1 || num_chunks != 1 || n_sub < 1) n_sub = 1;
+  pl.n_sub = n_sub;
   g.num_chunks = num_chunks;
   g.chunk_len = L / num_chunks;  // tail dropped, as ag-build/cl/multiexp.cl:235
   g.L = g.chunk_len * num_chunks;
@@ -98,86 +104,111 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   pl.PG = TG / pl.RW;
   const uint32_t n_tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
   size_t b = 0;
-  b += Arena::padded((size_t)(g.NB + 1) * 4) * 3;                            // counts, bucket_start, cursor
-  b += Arena::padded((size_t)(n_tiles + 1) * 4);                             // tile sums + grand total
-  b += Arena::padded(pl.E_max * 4);                                          // entries
-  b += Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));              // bucket accumulators
-  b += Arena::padded((size_t)2 * pl.n_slices * n_lines * sizeof(Xyzz<F>));   // slice partials
+  // per sub-batch (n_sub == 1: the whole call); sizes are upper bounds for every sub-batch
+  b += n_sub * Arena::padded((size_t)(g.NB + 1) * 4) * 3;                    // counts, bucket_start, cursor
+  b += n_sub * Arena::padded((size_t)(n_tiles + 1) * 4);                     // tile sums + grand total
+  b += n_sub * Arena::padded((pl.E_max / n_sub + g.W) * 4);                  // entries
+  b += n_sub * Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));      // bucket accumulators
+  b += n_sub * Arena::padded((size_t)2 * (pl.n_slices / n_sub + 2) * n_lines * sizeof(Xyzz<F>));  // slice partials
   b += 2 * Arena::padded((size_t)pl.n_tasks * pl.W_sets * pl.PG * sizeof(Xyzz<F>));  // group partials (ping-pong)
-  b += Arena::padded((size_t)(n_lines + (size_t)n_lines * (pl.n_slices / HEAVY_SPAN + 1)) * 4);  // heavy-bucket work list
+  b += n_sub * Arena::padded((size_t)(n_lines + (size_t)n_lines * (pl.n_slices / HEAVY_SPAN + 1)) * 4);  // heavy-bucket work list
   pl.scratch_bytes = b;
   return MSM_OK;
 }
 
 // Enqueue one whole MSM batch on dc.stream.  d_scalars / d_out are device pointers.  No sync.
+// pl.n_sub > 1 (single-task calls only): the scalar row is processed in n_sub contiguous
+// sub-batches, each sorted and accumulated into its own bucket array as soon as sub_ready[k] has
+// fired (its scalars have arrived from the host); the reduction sums the arrays.
 template <class F>
 int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<F>* d_bases,
-                uint32_t line_stride, const uint32_t* d_scalars, ApiJacobian<F>* d_out, bool timed) {
+                uint32_t line_stride, const uint32_t* d_scalars, ApiJacobian<F>* d_out, bool timed,
+                cudaEvent_t* sub_ready = nullptr) {
   const Geometry& g = pl.geo;
   CU_TRY(ctx, dc.arena.ensure(pl.scratch_bytes));
   const uint32_t n_tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
-  uint32_t* counts = dc.arena.take<uint32_t>(g.NB + 1);
-  uint32_t* bucket_start = dc.arena.take<uint32_t>(g.NB + 1);
-  uint32_t* cursor = dc.arena.take<uint32_t>(g.NB + 1);
-  uint32_t* tile_sums = dc.arena.take<uint32_t>(n_tiles + 1);
-  uint32_t* entries = dc.arena.take<uint32_t>(pl.E_max);
-  Xyzz<F>* bucket_acc = dc.arena.take<Xyzz<F>>((size_t)g.NB * pl.n_lines);
-  Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * pl.n_slices * pl.n_lines);
+  const uint32_t n_sub = pl.n_sub;
+  const uint32_t tb = 128;
+  cudaStream_t st = dc.stream;
+  Xyzz<F>* bucket_acc = dc.arena.take<Xyzz<F>>((size_t)g.NB * pl.n_lines * n_sub);
   Xyzz<F>* group_partials = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
   Xyzz<F>* group_partials2 = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
-  const uint32_t heavy_cap = pl.n_slices / HEAVY_SPAN + 1;
-  uint32_t* heavy_count = dc.arena.take<uint32_t>(pl.n_lines + (size_t)pl.n_lines * heavy_cap);
-  uint32_t* heavy_list = heavy_count + pl.n_lines;
-  cudaStream_t st = dc.stream;
 
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
-  // --- sort: histogram, scan, scatter
-  CU_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.NB + 1) * 4, st));
-  const uint32_t db = 256, dg = (g.L + db - 1) / db;
-  k_digits<false><<<dg, db, 0, st>>>(d_scalars, g, counts, nullptr, 0u, g.NB);
-  k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
-  k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
-  k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(bucket_start, g.NB, tile_sums, tile_sums + n_tiles, cursor);
-  {
-    // scatter in bucket-range passes: each pass writes a bounded slice of `entries` at random, which
-    // the 126 MB L2 partly absorbs; every pass re-reads the scalars (sequential)
-    // (measured at 2^24: 4 passes best for c = 22 folded, 1-2 for c = 16; every pass repeats the
-    // digit extraction, so more passes stop paying quickly)
-    uint32_t passes = (uint32_t)((pl.E_max * 4 + (200u << 20) - 1) / (200u << 20));
-    if (const char* env = getenv("MSM_B200_SCATTER_PASSES")) passes = (uint32_t)atoi(env);
-    passes = passes < 1 ? 1 : (passes > 8 ? 8 : passes);
-    const uint32_t per = (g.NB + passes - 1) / passes;
-    for (uint32_t ps = 0; ps < passes; ps++) {
-      const uint32_t lo = ps * per, hi = lo + per < g.NB ? lo + per : g.NB;
-      if (lo >= hi) break;
-      k_digits<true><<<dg, db, 0, st>>>(d_scalars, g, cursor, entries, lo, hi);
-      dc.launches += 1;
+  const uint32_t L_sub = (g.L + n_sub - 1) / n_sub;
+  for (uint32_t sb = 0; sb < n_sub; sb++) {
+    Geometry sg = g;
+    uint32_t S = pl.S, n_slices = pl.n_slices;
+    uint64_t E_max = pl.E_max;
+    const uint32_t first = sb * L_sub;
+    if (n_sub > 1) {
+      sg.L = first < g.L ? (g.L - first < L_sub ? g.L - first : L_sub) : 0;
+      sg.chunk_len = sg.L ? sg.L : 1;
+      sg.point_offset = g.fold ? first : 0;
+      E_max = (uint64_t)sg.L * g.W;
+      n_slices = (uint32_t)((E_max + S - 1) / S);
+      if (n_slices == 0) n_slices = 1;
     }
-  }
-  if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
-  if (aborted(ctx)) return MSM_ERR_ABORTED;
-  // --- accumulate
-  {
-    const uint32_t tb = 128;
-    dim3 grid((pl.n_slices + tb - 1) / tb, pl.n_lines);
-    k_accumulate<F><<<grid, tb, 0, st>>>(d_bases, line_stride, entries, bucket_start, g.NB,
-                                         bucket_start + g.NB, pl.S, pl.n_slices, bucket_acc, partials);
+    uint32_t* counts = dc.arena.take<uint32_t>(g.NB + 1);
+    uint32_t* bucket_start = dc.arena.take<uint32_t>(g.NB + 1);
+    uint32_t* cursor = dc.arena.take<uint32_t>(g.NB + 1);
+    uint32_t* tile_sums = dc.arena.take<uint32_t>(n_tiles + 1);
+    uint32_t* entries = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
+    Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * (pl.n_slices / n_sub + 2) * pl.n_lines);
+    const uint32_t heavy_cap = n_slices / HEAVY_SPAN + 1;
+    uint32_t* heavy_count = dc.arena.take<uint32_t>(pl.n_lines + (size_t)pl.n_lines * (pl.n_slices / HEAVY_SPAN + 1));
+    uint32_t* heavy_list = heavy_count + pl.n_lines;
+    Xyzz<F>* acc_sb = bucket_acc + (size_t)sb * g.NB * pl.n_lines;
+    const uint32_t* sc_sb = d_scalars + (size_t)first * 8;
+    const PackedAffine<F>* bases_sb = (n_sub > 1 && !g.fold) ? d_bases + first : d_bases;
+
+    if (sub_ready) CU_TRY(ctx, cudaStreamWaitEvent(st, sub_ready[sb], 0));
+    // --- sort: histogram, scan, scatter
+    CU_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.NB + 1) * 4, st));
+    const uint32_t db = 256, dg = (sg.L + db - 1) / db;
+    if (dg) k_digits<false><<<dg, db, 0, st>>>(sc_sb, sg, counts, nullptr, 0u, g.NB);
+    k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
+    k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
+    k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(bucket_start, g.NB, tile_sums, tile_sums + n_tiles, cursor);
+    {
+      // scatter in bucket-range passes: each pass writes a bounded slice of `entries` at random,
+      // which the 126 MB L2 partly absorbs; every pass re-reads the scalars (sequential).  Measured
+      // at 2^24: 4 passes best for c = 22 folded, 1-2 for c = 16; every pass repeats the digit
+      // extraction, so more passes stop paying quickly.
+      uint32_t passes = (uint32_t)((E_max * 4 + (200u << 20) - 1) / (200u << 20));
+      if (const char* env = getenv("MSM_B200_SCATTER_PASSES")) passes = (uint32_t)atoi(env);
+      passes = passes < 1 ? 1 : (passes > 8 ? 8 : passes);
+      pl.scatter_passes = passes;
+      const uint32_t per = (g.NB + passes - 1) / passes;
+      for (uint32_t ps = 0; ps < passes && dg; ps++) {
+        const uint32_t lo = ps * per, hi = lo + per < g.NB ? lo + per : g.NB;
+        if (lo >= hi) break;
+        k_digits<true><<<dg, db, 0, st>>>(sc_sb, sg, cursor, entries, lo, hi);
+        dc.launches += 1;
+      }
+    }
+    if (timed && sb == 0) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
+    if (aborted(ctx)) return MSM_ERR_ABORTED;
+    // --- accumulate
+    dim3 grid((n_slices + tb - 1) / tb, pl.n_lines);
+    k_accumulate<F><<<grid, tb, 0, st>>>(bases_sb, line_stride, entries, bucket_start, g.NB, bucket_start + g.NB,
+                                         S, n_slices, acc_sb, partials);
     dim3 fgrid((g.NB + tb - 1) / tb, pl.n_lines);
     CU_TRY(ctx, cudaMemsetAsync(heavy_count, 0, (size_t)pl.n_lines * 4, st));
-    k_fixup<F><<<fgrid, tb, 0, st>>>(bucket_start, g.NB, pl.S, pl.n_slices, bucket_acc, partials, heavy_count,
-                                     heavy_list, heavy_cap);
+    k_fixup<F><<<fgrid, tb, 0, st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials, heavy_count, heavy_list,
+                                     heavy_cap);
     dim3 hgrid(heavy_cap < 296 ? heavy_cap : 296, pl.n_lines);
-    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, pl.S, pl.n_slices, bucket_acc,
-                                                             partials, heavy_count, heavy_list, heavy_cap);
+    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials,
+                                                             heavy_count, heavy_list, heavy_cap);
+    dc.launches += 8;
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[3], st));
   if (aborted(ctx)) return MSM_ERR_ABORTED;
   // --- reduce + combine
   {
-    const uint32_t tb = 128;
     const uint64_t n_threads = (uint64_t)g.NB * pl.n_lines / pl.Q;
     k_bucket_reduce<F><<<(uint32_t)((n_threads + tb - 1) / tb), tb, tb * sizeof(Xyzz<F>), st>>>(
-        bucket_acc, (uint32_t)n_threads, g.B, pl.Q, pl.RW, group_partials);
+        bucket_acc, (uint32_t)n_threads, g.B, pl.Q, pl.RW, group_partials, n_sub, (size_t)g.NB * pl.n_lines);
     const uint32_t Ws = pl.W_sets;
     // the PG partials of every (task, window) group shrink 1024-fold per pass
     uint32_t pg = pl.PG;
@@ -198,7 +229,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     }
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[4], st));
-  dc.launches += 10;
+  dc.launches += 2;
   CU_TRY(ctx, cudaGetLastError());
   return MSM_OK;
 }
@@ -215,6 +246,8 @@ inline void collect_timings(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, bool ha
   t.num_windows = pl.geo.W;
   t.num_entries = pl.E_max;
   t.kernel_launches = dc.launches;
+  t.scatter_passes = pl.scatter_passes;
+  t.sub_batches = pl.n_sub;
 }
 
 template <class F>
@@ -233,8 +266,19 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   CU_TRY(ctx, cudaSetDevice(dc.dev));
   const msm_bases::Shard& sh0 = bases->shards[0];
   const bool use_table = sh0.table && num_chunks == 1 && n_lines == 1 && L == sh0.n && !ctx->window_override;
+  // Host scalars of one large single-task call arrive in n_sub chunks on a copy stream while the
+  // previous chunk is already being sorted and accumulated (the 32 B/scalar upload is ~20 % of the
+  // call otherwise).
+  uint32_t n_sub = 1;
+  // Measured at 2^24 with the c = 22 table: 2 sub-batches 47.3 ms end to end, 1: 48.8, 4: 50.1, 8: 57.1 --
+  // every sub-batch repeats the per-bucket work, so only the coarsest split pays.
+  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 23)) n_sub = 2;
+  if (const char* env = getenv("MSM_B200_PIPELINE")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= 8 && !device_io && num_chunks == 1 && n_lines == 1) n_sub = (uint32_t)v;
+  }
   Plan pl;
-  int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0);
+  int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0, n_sub);
   if (rc) return rc;
   if (aborted(ctx)) return MSM_ERR_ABORTED;
   const uint32_t* d_scalars;
@@ -248,11 +292,25 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
     uint32_t* ds = dc.io.take<uint32_t>(L * 8);
     d_out = dc.io.take<ApiJacobian<F>>(pl.n_tasks);
     CU_TRY(ctx, cudaEventRecord(dc.ev[0], dc.stream));
-    CU_TRY(ctx, cudaMemcpyAsync(ds, scalars, L * 32, cudaMemcpyHostToDevice, dc.stream));
+    if (pl.n_sub > 1) {
+      // the copy stream must not overwrite the staging area while an earlier call still reads it
+      CU_TRY(ctx, cudaStreamWaitEvent(dc.copy_stream, dc.ev[0], 0));
+      const size_t L_sub = (pl.geo.L + pl.n_sub - 1) / pl.n_sub;
+      for (uint32_t sb = 0; sb < pl.n_sub; sb++) {
+        const size_t first = std::min((size_t)sb * L_sub, (size_t)L);
+        const size_t cnt = std::min(L_sub, (size_t)L - first);
+        if (cnt)
+          CU_TRY(ctx, cudaMemcpyAsync(ds + first * 8, static_cast<const char*>(scalars) + first * 32, cnt * 32,
+                                      cudaMemcpyHostToDevice, dc.copy_stream));
+        CU_TRY(ctx, cudaEventRecord(dc.ev_copy[sb], dc.copy_stream));
+      }
+    } else {
+      CU_TRY(ctx, cudaMemcpyAsync(ds, scalars, L * 32, cudaMemcpyHostToDevice, dc.stream));
+    }
     d_scalars = ds;
   }
   rc = enqueue_msm<F>(ctx, dc, pl, static_cast<const PackedAffine<F>*>(use_table ? sh0.table : sh0.ptr), (uint32_t)L,
-                      d_scalars, d_out, true);
+                      d_scalars, d_out, true, (!device_io && pl.n_sub > 1) ? dc.ev_copy : nullptr);
   if (rc) {
     cudaStreamSynchronize(dc.stream);
     return rc;

@@ -32,6 +32,7 @@ struct Geometry {
   uint32_t scalar_bits;
   uint32_t fold;       // 1: bases are a window table T[w][i] = 2^(c w) P_i, all windows share one bucket set
   uint32_t table_stride;  // points per window in the table (= L)
+  uint32_t point_offset;  // folded sub-batches: index of this batch's first point in the table
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -119,7 +120,7 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
       } else {
         pos = atomicAdd(&counts_or_cursor[g], 1u);
       }
-      const uint32_t idx = geo.fold ? w * geo.table_stride + i : i;
+      const uint32_t idx = geo.fold ? w * geo.table_stride + geo.point_offset + i : i;
       entries[pos] = idx | (neg ? 0x80000000u : 0u);
     } else {
       if (!aggregate) atomicAdd(&counts_or_cursor[g], 1u);
@@ -401,7 +402,7 @@ k_reduce_points(const Xyzz<F>* __restrict__ in, uint32_t count, uint32_t out_cou
 template <class F>
 __global__ void __launch_bounds__(128)
 k_bucket_reduce(const Xyzz<F>* __restrict__ bucket_acc, uint32_t n_threads, uint32_t B, uint32_t Q,
-                uint32_t RW, Xyzz<F>* __restrict__ out) {
+                uint32_t RW, Xyzz<F>* __restrict__ out, uint32_t n_arrays, size_t array_stride) {
   extern __shared__ uint4 smem_raw[];
   Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,7 +412,8 @@ k_bucket_reduce(const Xyzz<F>* __restrict__ bucket_acc, uint32_t n_threads, uint
     const uint32_t b0 = (uint32_t)(f % B);  // weight of bucket f+k is b0 + k + 1
     Xyzz<F> run = xyzz_inf<F>();
     for (int k = (int)Q - 1; k >= 0; k--) {
-      run = xyzz_add<F>(run, load_vec(&bucket_acc[f + k]));
+      // sub-batches of a pipelined call each filled their own copy of the bucket array
+      for (uint32_t a = 0; a < n_arrays; a++) run = xyzz_add<F>(run, load_vec(&bucket_acc[a * array_stride + f + k]));
       res = xyzz_add<F>(res, run);
     }
     if (b0) res = xyzz_add<F>(res, xyzz_mul_small<F>(run, b0));

@@ -154,6 +154,27 @@ def run_reference(args, rank):
     }))
 
 
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError):
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(curve, log_n, n_local):
+    """dram bytes per k_accumulate launch from the committed ncu --set full capture of the same
+    workload (profiles/ncu_traffic.json); null when no capture matches this configuration."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            for e in json.load(f)["captures"]:
+                if e["curve"] == curve and e["log_n"] == log_n and e["points_per_gpu"] == n_local:
+                    return e["k_accumulate_dram_bytes_per_launch"], e["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
+
+
 def to_affine_bytes(lib, h, jac, fq):
     import numpy as np
 
@@ -333,6 +354,20 @@ def main():
                     "peak_source": "148 SMs x 64 int32-multiply lanes/clk x 1.965 GHz; tools/imad_peak.cu measured "
                                    "1.852e13 MAC/s (99.5 % of it) on this pool; MEASURED_PEAKS.json has no integer figure",
                     "whole_step_frac": value / world * MACS_PER_POINT[curve] / IMAD_PEAK_NOMINAL}
+        traffic, traffic_src = ncu_traffic(curve, args.log_n, n_local)
+        roofline["traffic"] = traffic
+        roofline["traffic_source"] = traffic_src
+        roofline["algorithmic_gather_bytes_per_launch"] = n_local * t_last["num_windows"] * 2 * fq
+        # sort phase (digit decomposition + histogram + scatter) against HBM
+        peaks, peak_src = measured_peaks()
+        sort_bytes = n_local * 32 * (1 + t_last["scatter_passes"]) + n_local * t_last["num_windows"] * 4
+        sort_gbs = sort_bytes / (t_last["sort_ms"] * 1e-3) / 1e9 if t_last["sort_ms"] > 0 else None
+        roofline_sort = {"bound": "hbm", "kernels": "k_digits<count> + scan + k_digits<scatter> x passes",
+                         "achieved": sort_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": (sort_gbs / peaks["hbm_gbs"]) if sort_gbs else None, "peak_source": peak_src,
+                         "algorithmic_bytes": sort_bytes, "phase_ms": t_last["sort_ms"],
+                         "note": "32 B/scalar read per pass + 4 B written per digit; the phase is bound by L2 "
+                                 "atomics and 4-byte scattered writes, not by HBM bandwidth (DESIGN.md section 9)"}
         same = bool((to_affine_bytes(lib, h, result_dev, fq) == to_affine_bytes(lib, h, result_e2e, fq)).all())
         name = "BN254 G1" if curve == 0 else "BLS12-381 G1"
         out = {
@@ -354,6 +389,7 @@ def main():
                             "ag_cuda_ec::multiple_multiexp"},
             "gpu_launches": int(launches + (args.steps if world > 1 else 0)),
             "roofline": roofline,
+            "roofline_sort": roofline_sort,
             "phases_ms": {k: round(t_last[k], 3) for k in ("sort_ms", "accumulate_ms", "reduce_ms", "total_ms")},
             "clocks": clocks,
             "paths_agree": same,

@@ -65,6 +65,8 @@ typedef struct {
   uint32_t num_windows;
   uint64_t num_entries;   /* non-zero digits sorted */
   uint64_t kernel_launches;
+  uint32_t scatter_passes; /* bucket-range passes of the scatter kernel */
+  uint32_t sub_batches;    /* > 1: host scalars were uploaded and processed in pipelined sub-batches */
 } msm_timings;
 
 /* ---- contexts -------------------------------------------------------------------------- */

@@ -34,6 +34,8 @@ pub struct msm_timings {
     pub num_windows: u32,
     pub num_entries: u64,
     pub kernel_launches: u64,
+    pub scatter_passes: u32,
+    pub sub_batches: u32,
 }
 
 extern "C" {
