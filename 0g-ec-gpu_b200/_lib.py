@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_LIB = os.path.join(_HERE, "libmsm_b200.so")
+_LIB = os.environ.get("MSM_B200_LIB") or os.path.join(_HERE, "libmsm_b200.so")  # override: A/B builds only
 _HEADER = os.path.join(_ROOT, "include", "msm_b200.h")
 
 BN254_G1 = 0

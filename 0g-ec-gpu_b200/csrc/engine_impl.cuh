@@ -46,7 +46,8 @@ struct Plan {
   uint32_t n_lines, S, n_slices, Q, RW, PG, n_tasks;
   uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
   uint32_t n_sub;   // sub-batches of a pipelined single-task call (each fills its own bucket array)
-  mutable uint32_t scatter_passes = 1;  // filled in by enqueue_msm
+  mutable uint32_t scatter_passes = 1;  // filled in by enqueue_msm (0: two-level partition scatter)
+  bool partition;   // large calls: two-level scatter through a (bucket id, entry) temporary
   uint64_t E_max;
   size_t scratch_bytes;
 };
@@ -108,6 +109,10 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   b += n_sub * Arena::padded((size_t)(g.NB + 1) * 4) * 3;                    // counts, bucket_start, cursor
   b += n_sub * Arena::padded((size_t)(n_tiles + 1) * 4);                     // tile sums + grand total
   b += n_sub * Arena::padded((pl.E_max / n_sub + g.W) * 4);                  // entries
+  // measured slower than the bucket-range passes on B200 (2^24, c = 22: 6.8 vs 5.2 ms): off unless asked for
+  pl.partition = false;
+  if (const char* env = getenv("MSM_B200_PARTITION")) pl.partition = atoi(env) != 0;
+  if (pl.partition) b += n_sub * (2 * Arena::padded((pl.E_max / n_sub + g.W) * 4) + Arena::padded(4096 * 4));  // tmp_g, tmp_v, bin cursors
   b += n_sub * Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));      // bucket accumulators
   b += n_sub * Arena::padded((size_t)2 * (pl.n_slices / n_sub + 2) * n_lines * sizeof(Xyzz<F>));  // slice partials
   b += 2 * Arena::padded((size_t)pl.n_tasks * pl.W_sets * pl.PG * sizeof(Xyzz<F>));  // group partials (ping-pong)
@@ -166,15 +171,36 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     // --- sort: histogram, scan, scatter
     CU_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.NB + 1) * 4, st));
     const uint32_t db = 256, dg = (sg.L + db - 1) / db;
-    if (dg) k_digits<false><<<dg, db, 0, st>>>(sc_sb, sg, counts, nullptr, 0u, g.NB);
+    if (dg) launch_digits<false>(dg, db, st, sc_sb, sg, counts, nullptr, 0u, g.NB);
     k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
     k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
     k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(bucket_start, g.NB, tile_sums, tile_sums + n_tiles, cursor);
-    {
+    if (pl.partition && dg) {
+      // two-level scatter (kernels.cuh): partition by the high bits of the bucket id, then place
+      uint32_t* tmp_g = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
+      uint32_t* tmp_v = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
+      uint32_t* bin_cursor = dc.arena.take<uint32_t>(4096);
+      uint32_t bins = 16;
+      while (bins < 1024 && (uint64_t)bins * (4u << 20) < E_max * 4) bins <<= 1;  // ~4 MB of entries per bin
+      uint32_t nb_log = 0;
+      while ((1ull << nb_log) < g.NB) nb_log++;
+      uint32_t bins_log = 0;
+      while ((1u << bins_log) < bins) bins_log++;
+      const uint32_t bin_shift = nb_log > bins_log ? nb_log - bins_log : 0;
+      const uint32_t n_bins = (uint32_t)(((uint64_t)g.NB + (1ull << bin_shift) - 1) >> bin_shift);
+      uint32_t tile = 12288 / g.W;
+      tile = tile > 1024 ? 1024 : (tile < 64 ? 64 : tile);
+      const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * g.W) * 4;
+      CU_TRY(ctx, cudaMemsetAsync(bin_cursor, 0, (size_t)n_bins * 4, st));
+      CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, sc_sb, sg, tile, bin_shift, n_bins, bucket_start,
+                                   bin_cursor, tmp_g, tmp_v));
+      k_final_scatter<<<(uint32_t)((E_max + 255) / 256), 256, 0, st>>>(tmp_g, tmp_v, bucket_start + g.NB, cursor, entries);
+      pl.scatter_passes = 0;
+      dc.launches += 2;
+    } else {
       // scatter in bucket-range passes: each pass writes a bounded slice of `entries` at random,
       // which the 126 MB L2 partly absorbs; every pass re-reads the scalars (sequential).  Measured
-      // at 2^24: 4 passes best for c = 22 folded, 1-2 for c = 16; every pass repeats the digit
-      // extraction, so more passes stop paying quickly.
+      // at 2^24: 4 passes best for c = 22 folded, 1-2 for c = 16.
       uint32_t passes = (uint32_t)((E_max * 4 + (200u << 20) - 1) / (200u << 20));
       if (const char* env = getenv("MSM_B200_SCATTER_PASSES")) passes = (uint32_t)atoi(env);
       passes = passes < 1 ? 1 : (passes > 8 ? 8 : passes);
@@ -183,7 +209,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
       for (uint32_t ps = 0; ps < passes && dg; ps++) {
         const uint32_t lo = ps * per, hi = lo + per < g.NB ? lo + per : g.NB;
         if (lo >= hi) break;
-        k_digits<true><<<dg, db, 0, st>>>(sc_sb, sg, cursor, entries, lo, hi);
+        launch_digits<true>(dg, db, st, sc_sb, sg, cursor, entries, lo, hi);
         dc.launches += 1;
       }
     }

@@ -77,6 +77,29 @@ template <class F> MSM_D void for_each_digit(const uint32_t k[8], uint32_t c, ui
   }
 }
 
+// Same decomposition with the window size known at compile time: every digit is one funnel shift
+// and one mask on registers (the generic loop above spends ~3x the instructions on 64-bit buffer
+// shifts; with 4-5 decomposition passes per call that was ~2 ms of a 2^24 MSM).
+template <int C, class F> MSM_D void for_each_digit_c(const uint32_t k[8], uint32_t W, F&& f) {
+  constexpr uint32_t half = 1u << (C - 1);
+  constexpr uint32_t mask = (1u << C) - 1u;
+  constexpr int MAXW = (256 + C - 1) / C + 1;
+  uint32_t carry = 0;
+#pragma unroll
+  for (int w = 0; w < MAXW; w++) {
+    if ((uint32_t)w >= W) break;
+    const int bit = w * C, word = bit >> 5, sh = bit & 31;
+    const uint32_t lo = word < 8 ? k[word < 8 ? word : 0] : 0u;
+    const uint32_t hi = word + 1 < 8 ? k[word + 1 < 8 ? word + 1 : 0] : 0u;
+    const uint32_t raw = (__funnelshift_r(lo, hi, sh) & mask) + carry;
+    carry = raw > half;
+    if (raw != 0 && raw != (1u << C)) {
+      if (carry) f((uint32_t)w, (1u << C) - raw, true);
+      else f((uint32_t)w, raw, false);
+    }
+  }
+}
+
 MSM_D void load_scalar(const uint32_t* scalars, uint32_t i, uint32_t k[8]) {
   const uint4* p = reinterpret_cast<const uint4*>(scalars) + 2 * (size_t)i;
   uint4 a = __ldg(p), b = __ldg(p + 1);
@@ -87,7 +110,7 @@ MSM_D void load_scalar(const uint32_t* scalars, uint32_t i, uint32_t k[8]) {
 // SCATTER = false: counts[g]++ ;  SCATTER = true: entries[cursor[g]++] = i | sign<<31
 // g_lo / g_hi: only digits whose bucket id lies in [g_lo, g_hi) are handled; the scatter runs in
 // several such passes so that the randomly written slice of `entries` stays resident in the L2.
-template <bool SCATTER>
+template <bool SCATTER, int C>
 __global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
                          uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries,
                          uint32_t g_lo, uint32_t g_hi) {
@@ -97,7 +120,7 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
   load_scalar(scalars, i, k);
   const uint32_t task = i / geo.chunk_len;
   const uint32_t base = task * geo.W;
-  for_each_digit(k, geo.c, geo.W, [&](uint32_t w, uint32_t bucket, bool neg) {
+  auto body = [&](uint32_t w, uint32_t bucket, bool neg) {
     const uint32_t g = geo.fold ? (bucket - 1) : (base + w) * geo.B + (bucket - 1);
     if (g < g_lo || g >= g_hi) return;
     // The top window only carries the few leftover scalar bits, so all points share a handful of
@@ -126,7 +149,25 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
       if (!aggregate) atomicAdd(&counts_or_cursor[g], 1u);
       else if ((threadIdx.x & 31) == leader_lane) atomicAdd(&counts_or_cursor[g], total);
     }
-  });
+  };
+  if (C == 0) for_each_digit(k, geo.c, geo.W, body);
+  else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
+}
+
+// launch with the window size as a template argument where an instantiation exists
+template <bool SCATTER>
+inline void launch_digits(uint32_t grid, uint32_t block, cudaStream_t st, const uint32_t* scalars, const Geometry& geo,
+                          uint32_t* counts_or_cursor, uint32_t* entries, uint32_t g_lo, uint32_t g_hi) {
+#define MSM_DIGITS_CASE(CC) \
+  case CC: k_digits<SCATTER, CC><<<grid, block, 0, st>>>(scalars, geo, counts_or_cursor, entries, g_lo, g_hi); break;
+  switch (geo.c) {
+    MSM_DIGITS_CASE(6) MSM_DIGITS_CASE(7) MSM_DIGITS_CASE(8) MSM_DIGITS_CASE(9) MSM_DIGITS_CASE(10)
+    MSM_DIGITS_CASE(11) MSM_DIGITS_CASE(12) MSM_DIGITS_CASE(13) MSM_DIGITS_CASE(14) MSM_DIGITS_CASE(15)
+    MSM_DIGITS_CASE(16) MSM_DIGITS_CASE(17) MSM_DIGITS_CASE(18) MSM_DIGITS_CASE(19) MSM_DIGITS_CASE(20)
+    MSM_DIGITS_CASE(21) MSM_DIGITS_CASE(22) MSM_DIGITS_CASE(23) MSM_DIGITS_CASE(24)
+    default: k_digits<SCATTER, 0><<<grid, block, 0, st>>>(scalars, geo, counts_or_cursor, entries, g_lo, g_hi);
+  }
+#undef MSM_DIGITS_CASE
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -208,6 +249,138 @@ static __global__ void k_scan_finish(uint32_t* __restrict__ out, uint32_t n, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two-level scatter (large calls).  A single-pass scatter writes 4-byte entries at random over
+// hundreds of MB: every write costs a 32-byte sector of DRAM traffic.  Instead:
+//   k_partition      each block decomposes a tile of scalars, groups its digits by the HIGH bits
+//                    of the bucket id in shared memory and appends every group to that high-bin's
+//                    region of a temporary (bucket id, entry) array in coalesced runs;
+//   k_final_scatter  walks the temporary array (now ordered by high-bin) and places every entry
+//                    with the usual cursor atomic -- the cursors and the destination slice touched
+//                    at any moment are a few MB and stay in the L2.
+// hb = g >> bin_shift; hb_region[hb] = bucket_start[hb << bin_shift] is where bin hb starts.
+// ---------------------------------------------------------------------------------------------
+constexpr int PART_BLOCK = 256;
+template <int C>
+__global__ void __launch_bounds__(PART_BLOCK)
+k_partition(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t tile, uint32_t bin_shift, uint32_t n_bins,
+            const uint32_t* __restrict__ bucket_start, uint32_t* __restrict__ bin_cursor,
+            uint32_t* __restrict__ tmp_g, uint32_t* __restrict__ tmp_v) {
+  extern __shared__ uint32_t part_smem[];
+  uint32_t* hist = part_smem;                 // [n_bins] counts, then running cursors
+  uint32_t* off = hist + n_bins;              // [n_bins] exclusive offsets inside the block
+  uint32_t* gbase = off + n_bins;             // [n_bins] global base of this block's run
+  uint32_t* stage_g = gbase + n_bins;         // [tile * W]
+  uint32_t* stage_v = stage_g + (size_t)tile * geo.W;
+  __shared__ uint32_t total_sh;
+  const uint32_t first = blockIdx.x * tile;
+  for (uint32_t b = threadIdx.x; b < n_bins; b += PART_BLOCK) hist[b] = 0;
+  __syncthreads();
+  // pass 1: histogram of high bins
+  for (uint32_t t = threadIdx.x; t < tile; t += PART_BLOCK) {
+    const uint32_t i = first + t;
+    if (i >= geo.L) break;
+    uint32_t k[8];
+    load_scalar(scalars, i, k);
+    const uint32_t base = (i / geo.chunk_len) * geo.W;
+    auto body = [&](uint32_t w, uint32_t bucket, bool) {
+      const uint32_t g = geo.fold ? (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+      atomicAdd(&hist[g >> bin_shift], 1u);
+    };
+    if (C == 0) for_each_digit(k, geo.c, geo.W, body);
+    else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
+  }
+  __syncthreads();
+  // exclusive scan of the bins (n_bins <= 4 * PART_BLOCK), one global reservation per non-empty bin
+  {
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint32_t b = threadIdx.x * 4 + q;
+      v[q] = b < n_bins ? hist[b] : 0;
+      sum += v[q];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(sum, &total);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint32_t b = threadIdx.x * 4 + q;
+      if (b < n_bins) {
+        off[b] = run;
+        gbase[b] = v[q] ? bucket_start[b << bin_shift] + atomicAdd(&bin_cursor[b], v[q]) : 0;
+        hist[b] = 0;
+      }
+      run += v[q];
+    }
+    if (threadIdx.x == 0) total_sh = total;
+  }
+  __syncthreads();
+  // pass 2: same decomposition, place (g, entry) in the block-local bin order
+  for (uint32_t t = threadIdx.x; t < tile; t += PART_BLOCK) {
+    const uint32_t i = first + t;
+    if (i >= geo.L) break;
+    uint32_t k[8];
+    load_scalar(scalars, i, k);
+    const uint32_t base = (i / geo.chunk_len) * geo.W;
+    auto body = [&](uint32_t w, uint32_t bucket, bool neg) {
+      const uint32_t g = geo.fold ? (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+      const uint32_t hb = g >> bin_shift;
+      const uint32_t slot = off[hb] + atomicAdd(&hist[hb], 1u);
+      const uint32_t idx = geo.fold ? w * geo.table_stride + geo.point_offset + i : i;
+      stage_g[slot] = g;
+      stage_v[slot] = idx | (neg ? 0x80000000u : 0u);
+    };
+    if (C == 0) for_each_digit(k, geo.c, geo.W, body);
+    else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
+  }
+  __syncthreads();
+  // write every bin's run to its region: consecutive slots of one bin are consecutive in memory
+  const uint32_t total = total_sh;
+  for (uint32_t sidx = threadIdx.x; sidx < total; sidx += PART_BLOCK) {
+    const uint32_t g = stage_g[sidx];
+    const uint32_t hb = g >> bin_shift;
+    const uint32_t dst = gbase[hb] + (sidx - off[hb]);
+    tmp_g[dst] = g;
+    tmp_v[dst] = stage_v[sidx];
+  }
+}
+
+static __global__ void k_final_scatter(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp_v,
+                                       const uint32_t* __restrict__ E_ptr, uint32_t* __restrict__ cursor,
+                                       uint32_t* __restrict__ entries) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= __ldg(E_ptr)) return;
+  const uint32_t pos = atomicAdd(&cursor[__ldg(tmp_g + i)], 1u);
+  entries[pos] = __ldg(tmp_v + i);
+}
+
+template <int C> inline cudaError_t partition_set_smem(size_t bytes) {
+  return cudaFuncSetAttribute(k_partition<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+inline cudaError_t launch_partition(uint32_t grid, size_t smem, cudaStream_t st, const uint32_t* scalars,
+                                    const Geometry& geo, uint32_t tile, uint32_t bin_shift, uint32_t n_bins,
+                                    const uint32_t* bucket_start, uint32_t* bin_cursor, uint32_t* tmp_g, uint32_t* tmp_v) {
+  cudaError_t e = cudaSuccess;
+#define MSM_PART_CASE(CC)                                                                                        \
+  case CC:                                                                                                       \
+    e = partition_set_smem<CC>(smem);                                                                            \
+    if (e == cudaSuccess)                                                                                        \
+      k_partition<CC><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, bucket_start,       \
+                                                      bin_cursor, tmp_g, tmp_v);                                 \
+    break;
+  switch (geo.c) {
+    MSM_PART_CASE(16) MSM_PART_CASE(17) MSM_PART_CASE(18) MSM_PART_CASE(19) MSM_PART_CASE(20)
+    MSM_PART_CASE(21) MSM_PART_CASE(22) MSM_PART_CASE(23) MSM_PART_CASE(24)
+    default:
+      e = partition_set_smem<0>(smem);
+      if (e == cudaSuccess)
+        k_partition<0><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, bucket_start, bin_cursor,
+                                                       tmp_g, tmp_v);
+  }
+#undef MSM_PART_CASE
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------
 // 128-bit vector loads / stores of plain structs (sizeof multiple of 16, 16-byte aligned).
 // ---------------------------------------------------------------------------------------------
 template <class T> MSM_D void store_vec(T* dst, const T& v) {
@@ -264,8 +437,10 @@ MSM_D uint32_t find_bucket(const uint32_t* __restrict__ bucket_start, uint32_t N
 // ---------------------------------------------------------------------------------------------
 // Bucket accumulation.  Thread t of line `blockIdx.y` owns sorted entries [t*S, (t+1)*S).
 // ---------------------------------------------------------------------------------------------
+// Resident blocks per SM: 4 for 8-limb fields (106 registers), 3 for 12-limb fields (168 registers);
+// measured: 5 blocks (spills) gains nothing for BN254, forcing 4 on BLS12-381 costs 5 %.
 template <class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (F::N <= 9 ? 4 : 3))
 k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
              const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start,
              uint32_t NB, const uint32_t* __restrict__ E_ptr, uint32_t S, uint32_t n_slices,

@@ -243,6 +243,29 @@ def test_montgomery_scalars_on_device(engine, oracle, pyref, ws, curve):
     assert_same_points(oracle, curve, got, want, "montgomery scalars")
 
 
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("c,chunks", [(13, 1), (16, 1), (9, 16), (20, 1)])
+def test_two_level_scatter_path(engine, oracle, ws, curve, c, chunks, monkeypatch):
+    """The partition + final-scatter sort that large calls use, forced on a small adversarial
+    input (skewed buckets, identity bases) for generic and compile-time window sizes."""
+    monkeypatch.setenv("MSM_B200_PARTITION", "1")
+    n = 5000
+    pts, sc = adversarial_inputs(oracle, curve, n)
+    w = ws[curve]
+    w.set_window_bits(c)
+    try:
+        bases_gpu = engine.upload_multiexp_bases(w, pts)
+        got = engine.multiple_multiexp(w, bases_gpu, sc, chunks, 8, True)
+        assert w.timings()["scatter_passes"] == 0
+    finally:
+        w.set_window_bits(0)
+    assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc, chunks), f"partition c={c}")
+    # and through a window table
+    bases_gpu.precompute(14)
+    got = engine.multiple_multiexp(w, bases_gpu, sc, 1, 8, True)
+    assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc, 1), "partition + table")
+
+
 def test_bn254_batched_4096(engine, oracle, ws):
     """Shape of ag-cuda-ec/benches/multiexp.rs:19-22,56 scaled down: 64 MSMs of 2^12 points."""
     curve, chunks, cl = 0, 64, 4096
