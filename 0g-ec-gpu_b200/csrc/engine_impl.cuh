@@ -95,7 +95,7 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   {
     const uint64_t total_buckets = (uint64_t)g.NB * n_lines;
     uint32_t Q = 8;
-    while (Q < 256 && total_buckets / Q > 131072) Q <<= 1;
+    while (Q < 256 && total_buckets / Q > 32768) Q <<= 1;  // measured: 2^21 buckets -> Q = 64, 2^18 -> Q = 8
     if (const char* env = getenv("MSM_B200_REDUCE_Q")) Q = (uint32_t)atoi(env);
     while (Q > g.B) Q >>= 1;
     pl.Q = Q < 1 ? 1 : Q;

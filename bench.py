@@ -207,8 +207,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--curve", type=int, default=0, help="0 = BN254 G1 (headline), 1 = BLS12-381 G1")
-    ap.add_argument("--cpu-log-sample", type=int, default=21, help="cpu_baseline sample size (log2)")
-    ap.add_argument("--ref-log-sample", type=int, default=20, help="--impl reference sample per step (log2)")
+    ap.add_argument("--cpu-log-sample", type=int, default=23, help="cpu_baseline sample size (log2)")
+    ap.add_argument("--ref-log-sample", type=int, default=21, help="--impl reference sample per step (log2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-table", action="store_true",
                     help="skip msm_bases_precompute (window table next to the resident bases)")
