@@ -117,6 +117,7 @@ def load_library() -> ctypes.CDLL:
         "msm_bases_upload_sharded": ([vp, vp, sz, pp], i32),
         "msm_bases_from_device": ([vp, vp, sz, pp], i32),
         "msm_bases_precompute": ([vp, vp, u32], i32),
+        "msm_bases_precompute_chunked": ([vp, vp, sz], i32),
         "msm_bases_table_window": ([vp], u32),
         "msm_bases_size_bytes": ([vp], sz),
         "msm_bases_num_points": ([vp], sz),

@@ -241,14 +241,21 @@ int msm_bases_upload_sharded(msm_ctx* ctx, const void* xy, size_t n, msm_bases**
 int msm_bases_from_device(msm_ctx* ctx, const void* d_xy, size_t n, msm_bases** out) {
   return make_resident(ctx, d_xy, n, false, true, out);
 }
-int msm_bases_precompute(msm_ctx* ctx, msm_bases* b, uint32_t window_bits) {
+static int precompute_tables(msm_ctx* ctx, msm_bases* b, uint32_t window_bits, size_t chunk_len) {
   if (!ctx || !b || b->ctx != ctx) return MSM_ERR_INVALID;
   LOCK_OR_BUSY(ctx);
   for (auto& sh : b->shards) {
-    int rc = ctx->ops->build_table(ctx, sh, window_bits);
+    int rc = ctx->ops->build_table(ctx, sh, window_bits, chunk_len);
     if (rc != MSM_OK) return rc;
   }
   return MSM_OK;
+}
+int msm_bases_precompute(msm_ctx* ctx, msm_bases* b, uint32_t window_bits) {
+  return precompute_tables(ctx, b, window_bits, 0);
+}
+int msm_bases_precompute_chunked(msm_ctx* ctx, msm_bases* b, size_t chunk_len) {
+  if (chunk_len == 0) return MSM_ERR_INVALID;
+  return precompute_tables(ctx, b, 0, chunk_len);
 }
 uint32_t msm_bases_table_window(const msm_bases* b) { return (b && !b->shards.empty()) ? b->shards[0].table_c : 0; }
 size_t msm_bases_size_bytes(const msm_bases* b) { return b ? b->n * b->ctx->ops->api_point_bytes : 0; }

@@ -125,7 +125,8 @@ struct FieldOps {
   // d_api (device, API layout) -> d_packed (device, resident layout); enqueued on dc.stream
   int (*convert_bases)(msm_ctx*, DeviceCtx&, const void* d_api, size_t n, void* d_packed);
   // window table for one shard (allocates sh.table); c == 0: the engine's choice for shard-sized MSMs
-  int (*build_table)(msm_ctx*, msm_bases::Shard& sh, uint32_t c);
+  // (chunk_len == 0) or for tasks of chunk_len points
+  int (*build_table)(msm_ctx*, msm_bases::Shard& sh, uint32_t c, size_t chunk_len);
   int (*synth_points)(msm_ctx*, uint64_t seed, size_t start, size_t n, void* d_out);
   int (*test_fq)(msm_ctx*, int op, const void* a, const void* b, void* out, size_t count);
   int (*test_ec)(msm_ctx*, int op, const void* a, const void* b, void* out, size_t count);

@@ -20,7 +20,13 @@ namespace msm {
 // reference leaves this to the caller (window_size argument) or to calc_window_size
 // (ec-gpu-proxy/src/multiexp.rs:245-252); results never depend on it.
 // ---------------------------------------------------------------------------------------------
-inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_tasks_lines, size_t xyzz_bytes) {
+// cost of one bucket in the reduction, in field products (measured): with very many (task, window)
+// groups one thread owns a whole group and pays the two additions of the running sum; with few
+// groups the per-thread fix-up, the shared-memory tree and low occupancy triple that
+inline double reduce_cost_per_bucket(double n_groups) { return n_groups >= 32768.0 ? 34.0 : 90.0; }
+
+inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_tasks_lines, size_t xyzz_bytes,
+                              double* cost_out = nullptr) {
   double best = 1e300;
   uint32_t best_c = 2;
   for (uint32_t c = 2; c <= 22; c++) {
@@ -28,11 +34,32 @@ inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_task
     const double B = (double)(1u << (c - 1));
     const double bucket_bytes = (double)n_tasks_lines * W * B * (double)xyzz_bytes;
     if (bucket_bytes > 6e9) break;
-    // cost of one bucket in the reduction, in field products (measured): with very many (task,
-    // window) groups one thread owns a whole group and pays the two additions of the running sum;
-    // with few groups the per-thread fix-up, the shared-memory tree and low occupancy triple that
-    const double per_bucket = (double)n_tasks_lines * W >= 32768.0 ? 34.0 : 90.0;
+    const double per_bucket = reduce_cost_per_bucket((double)n_tasks_lines * W);
     const double cost = (double)W * ((double)chunk_len * 10.0 + B * per_bucket);
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  if (cost_out) *cost_out = best;
+  return best_c;
+}
+
+// Same figure for a folded window table of window size c: the W digits of a point all land in the
+// task's single bucket set, so the per-window reduction disappears.
+inline double fold_cost(uint32_t c, uint32_t chunk_len, uint32_t bits, uint64_t n_tasks_lines) {
+  const uint32_t W = (bits + 1 + c - 1) / c;
+  return (double)W * (double)chunk_len * 10.0 + (double)(1u << (c - 1)) * reduce_cost_per_bucket((double)n_tasks_lines);
+}
+// Window size of a table meant for tasks of chunk_len points (msm_bases_precompute_chunked).
+inline uint32_t choose_table_window(uint32_t chunk_len, uint32_t bits, uint64_t n_tasks_lines, uint64_t n_points) {
+  double best = 1e300;
+  uint32_t best_c = 0;
+  for (uint32_t c = 8; c <= 24; c++) {
+    const uint32_t W = (bits + 1 + c - 1) / c;
+    if ((uint64_t)W * n_points >= (1ull << 31) || W > (uint32_t)TABLE_MAX_W) continue;
+    if ((double)n_tasks_lines * (double)(1u << (c - 1)) * 128.0 > 12e9) break;
+    const double cost = fold_cost(c, chunk_len, bits, n_tasks_lines);
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -55,11 +82,11 @@ struct Plan {
 // table_c != 0: the bases are a window table built for window size table_c covering exactly L points
 template <class F>
 int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, Plan& pl, uint32_t table_c = 0,
-              uint32_t n_sub = 1) {
+              uint32_t n_sub = 1, uint32_t table_stride = 0) {
   if (L == 0 || num_chunks == 0 || n_lines == 0 || num_chunks > L) return MSM_ERR_INVALID;
   Geometry& g = pl.geo;
   g.fold = table_c ? 1 : 0;
-  g.table_stride = L;
+  g.table_stride = table_stride ? table_stride : L;
   g.point_offset = 0;
   if (n_lines != 1 || num_chunks != 1 || n_sub < 1) n_sub = 1;
   pl.n_sub = n_sub;
@@ -291,7 +318,23 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   DeviceCtx& dc = ctx->devs[0];
   CU_TRY(ctx, cudaSetDevice(dc.dev));
   const msm_bases::Shard& sh0 = bases->shards[0];
-  const bool use_table = sh0.table && num_chunks == 1 && n_lines == 1 && L == sh0.n && !ctx->window_override;
+  // A window table serves (i) the call it was built for -- one MSM over the whole shard -- and (ii) any
+  // chunked / multi-line call for which folding all windows of a task into one bucket set is cheaper
+  // than the plain per-window bucket sets at the window size the plain path would pick.
+  bool use_table = false;
+  if (sh0.table && !ctx->window_override && num_chunks >= 1 && num_chunks <= L) {
+    if (num_chunks == 1 && n_lines == 1 && L == sh0.n) {
+      use_table = true;
+    } else if (!getenv("MSM_B200_NO_CHUNK_TABLE")) {
+      const uint32_t chunk_len = (uint32_t)(L / num_chunks);
+      const uint64_t groups = (uint64_t)num_chunks * n_lines;
+      const double bucket_bytes = (double)groups * (double)(1u << (sh0.table_c - 1)) * (double)sizeof(Xyzz<F>);
+      double plain_cost = 0;
+      choose_window(chunk_len, scalar_bits(ctx->curve), groups, sizeof(Xyzz<F>), &plain_cost);
+      use_table = bucket_bytes <= 12e9 && (uint64_t)num_chunks << (sh0.table_c - 1) < (1ull << 31) &&
+                  fold_cost(sh0.table_c, chunk_len, scalar_bits(ctx->curve), groups) < plain_cost;
+    }
+  }
   // Host scalars of one large single-task call arrive in n_sub chunks on a copy stream while the
   // previous chunk is already being sorted and accumulated (the 32 B/scalar upload is ~20 % of the
   // call otherwise).
@@ -304,7 +347,8 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
     if (v >= 1 && v <= 8 && !device_io && num_chunks == 1 && n_lines == 1) n_sub = (uint32_t)v;
   }
   Plan pl;
-  int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0, n_sub);
+  int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0, n_sub,
+                        use_table ? (uint32_t)sh0.n : 0);
   if (rc) return rc;
   if (aborted(ctx)) return MSM_ERR_ABORTED;
   const uint32_t* d_scalars;
@@ -507,11 +551,16 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
 }
 
 // Window table for one resident shard (msm_bases_precompute).
-template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint32_t c) {
+template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint32_t c, size_t chunk_len) {
   if (sh.n == 0) return MSM_OK;
   DeviceCtx& dc = ctx->devs[sh.dev_idx];
   CU_TRY(ctx, cudaSetDevice(dc.dev));
   const uint32_t bits = scalar_bits(ctx->curve);
+  if (c == 0 && chunk_len != 0 && chunk_len < sh.n) {
+    // table for many tasks of chunk_len points each (msm_bases_precompute_chunked)
+    c = choose_table_window((uint32_t)chunk_len, bits, sh.n / chunk_len, sh.n);
+    if (c == 0) return MSM_ERR_TOO_LARGE;
+  }
   if (c == 0) {
     // all windows share one bucket set: cost = W * n mixed adds + 2^(c-1) * 2 full adds
     double best = 1e300;
@@ -527,7 +576,7 @@ template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint
     if (c == 0) return MSM_ERR_TOO_LARGE;
   }
   const uint32_t W = (bits + 1 + c - 1) / c;
-  if (c < 11 || c > 24 || W > TABLE_MAX_W || (uint64_t)W * sh.n >= (1ull << 31)) {
+  if (c < 8 || c > 24 || W > (uint32_t)TABLE_MAX_W || (uint64_t)W * sh.n >= (1ull << 31)) {
     set_error(ctx, "msm_bases_precompute: window size out of range for this shard");
     return MSM_ERR_INVALID;
   }

@@ -28,12 +28,13 @@ struct Geometry {
   uint32_t c;          // window bits
   uint32_t W;          // windows
   uint32_t B;          // buckets per (task, window) = 2^(c-1)
-  uint32_t NB;         // num_chunks * W * B   (folded: B)
+  uint32_t NB;         // num_chunks * W * B   (folded: num_chunks * B)
   uint32_t scalar_bits;
-  uint32_t fold;       // 1: bases are a window table T[w][i] = 2^(c w) P_i, all windows share one bucket set
-  uint32_t table_stride;  // points per window in the table (= L)
+  uint32_t fold;       // 1: bases are a window table T[w][i] = 2^(c w) P_i, all windows of a task share one bucket set
+  uint32_t table_stride;  // points per window in the table (= points of the resident shard)
   uint32_t point_offset;  // folded sub-batches: index of this batch's first point in the table
 };
+MSM_HD uint32_t task_of(uint32_t i, const Geometry& geo) { return geo.num_chunks == 1 ? 0u : i / geo.chunk_len; }
 
 // ---------------------------------------------------------------------------------------------
 // Signed-digit decomposition.  k = sum_w d_w 2^(c w),  d_w in [-(2^(c-1) - 1), 2^(c-1)].
@@ -121,7 +122,7 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
   const uint32_t task = i / geo.chunk_len;
   const uint32_t base = task * geo.W;
   auto body = [&](uint32_t w, uint32_t bucket, bool neg) {
-    const uint32_t g = geo.fold ? (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+    const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
     if (g < g_lo || g >= g_hi) return;
     // The top window only carries the few leftover scalar bits, so all points share a handful of
     // its buckets: aggregate those atomics per warp (one atomic per distinct bucket).
@@ -283,7 +284,7 @@ k_partition(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t tile, u
     load_scalar(scalars, i, k);
     const uint32_t base = (i / geo.chunk_len) * geo.W;
     auto body = [&](uint32_t w, uint32_t bucket, bool) {
-      const uint32_t g = geo.fold ? (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+      const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
       atomicAdd(&hist[g >> bin_shift], 1u);
     };
     if (C == 0) for_each_digit(k, geo.c, geo.W, body);
@@ -322,7 +323,7 @@ k_partition(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t tile, u
     load_scalar(scalars, i, k);
     const uint32_t base = (i / geo.chunk_len) * geo.W;
     auto body = [&](uint32_t w, uint32_t bucket, bool neg) {
-      const uint32_t g = geo.fold ? (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+      const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
       const uint32_t hb = g >> bin_shift;
       const uint32_t slot = off[hb] + atomicAdd(&hist[hb], 1u);
       const uint32_t idx = geo.fold ? w * geo.table_stride + geo.point_offset + i : i;
@@ -668,7 +669,7 @@ __global__ void k_convert_bases(const ApiAffine<F>* __restrict__ in, uint32_t n,
 // One thread per point: (W-1)*c doublings in XYZZ, then one shared inversion (Montgomery's trick
 // over the thread's W-1 results).  With the table every window of a large MSM lands in ONE bucket
 // set: no per-window bucket arrays and no Horner doublings at the end of each call.
-constexpr int TABLE_MAX_W = 24;
+constexpr int TABLE_MAX_W = 32;
 template <class F>
 __global__ void __launch_bounds__(64)
 k_build_tables(const PackedAffine<F>* __restrict__ bases, uint32_t n, uint32_t c, uint32_t W,

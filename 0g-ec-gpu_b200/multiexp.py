@@ -81,6 +81,15 @@ class DeviceData:
               cuda_style=True)
         return lib.msm_bases_table_window(self._h)
 
+    def precompute_chunked(self, chunk_len: int) -> int:
+        """Engine extension (msm_bases_precompute_chunked): window table sized for
+        multiple_multiexp calls whose tasks have chunk_len points each (the per-segment commitment
+        and AMT shapes).  Returns the table's window size."""
+        lib = load_library()
+        check(lib.msm_bases_precompute_chunked(self.workspace.handle, self._h, chunk_len), self.workspace.handle,
+              cuda_style=True)
+        return lib.msm_bases_table_window(self._h)
+
     def free(self):
         if self._h:
             load_library().msm_bases_free(self._h)

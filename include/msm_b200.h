@@ -105,14 +105,19 @@ int msm_bases_upload_sharded(msm_ctx* ctx, const void* xy_mont, size_t n_points,
 /* Same as msm_bases_upload with the source points already in device memory of device 0 (same
  * {x,y} Montgomery layout); the engine keeps its own resident copy, the source may be freed. */
 int msm_bases_from_device(msm_ctx* ctx, const void* d_xy_mont, size_t n_points, msm_bases** out);
-/* Optional, for bases that serve repeated LARGE single MSMs (num_chunks == 1, one line, all
- * points of a shard): build the window table T[w][i] = 2^(c w) P_i next to the resident copy
- * (W = ceil((bits+1)/c) times its size; window_bits == 0 lets the engine choose c).  Calls that
- * cover a whole shard then use one shared bucket set for all windows -- no per-window bucket
- * arrays, no Horner doublings; every other call shape keeps using the plain resident copy.
+/* Optional: build the window table T[w][i] = 2^(c w) P_i next to the resident copy
+ * (W = ceil((bits+1)/c) times its size; window_bits == 0 lets the engine choose c for one MSM over
+ * the whole shard; 8 <= c <= 24 otherwise).  With the table every window of a task lands in ONE
+ * bucket set -- no per-window bucket arrays, no Horner doublings.  Used by calls that cover a whole
+ * shard as one MSM, and by chunked / multi-line calls (the per-segment commitment and AMT shapes,
+ * ag-cuda-ec/benches/{multiexp,amt}.rs) whenever the engine's cost model says the folded form is
+ * cheaper than the plain one; every other call keeps using the plain resident copy.
  * Pure optimisation: results are unchanged.  The reference has no counterpart (its kernel walks
  * the windows of each scalar in separate threads, ag-build/cl/multiexp.cl:95-119). */
 int msm_bases_precompute(msm_ctx* ctx, msm_bases* b, uint32_t window_bits);
+/* Same with the window size chosen for tasks of chunk_len points each (multiple_multiexp with
+ * num_chunks = L / chunk_len), e.g. 4096 for ag-cuda-ec/benches/multiexp.rs:19-22. */
+int msm_bases_precompute_chunked(msm_ctx* ctx, msm_bases* b, size_t chunk_len);
 /* Window size of the table (0: none). */
 uint32_t msm_bases_table_window(const msm_bases* b);
 /* DeviceData::size (ag-cuda-proxy/src/params.rs:209): bytes. */

@@ -366,6 +366,7 @@ template <int N> struct Curve {
 
 static Curve<4> g_bn254;
 static Curve<6> g_bls381;
+static Field<4> g_bn254_fr, g_bls381_fr;  // scalar fields (EC-FFT twiddles, Montgomery form like arkworks' Fr)
 
 static void parse_hex(u64* out, int n, const char* hex) {
   memset(out, 0, sizeof(u64) * n);
@@ -396,6 +397,7 @@ static void init_curves() {
     g_bn254.fq.to_mont(g_bn254.gen.x, gx);
     g_bn254.fq.to_mont(g_bn254.gen.y, gy);
     g_bn254.ready = true;
+    g_bn254_fr.init(g_bn254.r);
   }
   {
     u64 p[6];
@@ -416,6 +418,7 @@ static void init_curves() {
     g_bls381.fq.to_mont(g_bls381.gen.x, gx);
     g_bls381.fq.to_mont(g_bls381.gen.y, gy);
     g_bls381.ready = true;
+    g_bls381_fr.init(g_bls381.r);
   }
   done.store(1);
 }
@@ -652,6 +655,61 @@ static void msm_naive(const Curve<N>& cv, const Aff<N>* bases, const u64* exps, 
   out = acc;
 }
 
+// k * P for a Jacobian P, k canonical little-endian (double-and-add, MSB first)
+template <int N>
+static void jac_scalar_mul(const Curve<N>& cv, Jac<N>& r, const Jac<N>& p, const u64* k, int words) {
+  Jac<N> acc;
+  cv.set_inf(acc);
+  for (int i = words * 64 - 1; i >= 0; i--) {
+    cv.dbl(acc, acc);
+    if ((k[i / 64] >> (i % 64)) & 1) cv.add(acc, acc, p);
+  }
+  r = acc;
+}
+
+// serial_ec_fft (ec-gpu-proxy/src/ec_fft_cpu.rs:12-57): bit-reversal, then log_n rounds of
+// butterflies t = w * a[k+j+m]; a[k+j+m] = a[k+j] - t; a[k+j] += t with w running over powers of
+// w_m = omega^(n/2m).  omega is an Fr element in Montgomery form.
+template <int N>
+static void ec_fft_serial(const Curve<N>& cv, const Field<4>& fr, Jac<N>* a, uint32_t log_n, const u64* omega_mont) {
+  const uint32_t n = 1u << log_n;
+  for (uint32_t k = 0; k < n; k++) {
+    uint32_t rk = 0, t = k;
+    for (uint32_t i = 0; i < log_n; i++) { rk = (rk << 1) | (t & 1); t >>= 1; }
+    if (k < rk) std::swap(a[k], a[rk]);
+  }
+  uint32_t m = 1;
+  for (uint32_t round = 0; round < log_n; round++) {
+    // w_m = omega^(n / 2m)
+    u64 w_m[4];
+    memcpy(w_m, fr.one, sizeof(w_m));
+    {
+      u64 base[4];
+      memcpy(base, omega_mont, sizeof(base));
+      for (uint32_t e = n / (2 * m); e; e >>= 1) {
+        if (e & 1) fr.mul(w_m, w_m, base);
+        fr.sqr(base, base);
+      }
+    }
+    for (uint32_t k = 0; k < n; k += 2 * m) {
+      u64 w[4];
+      memcpy(w, fr.one, sizeof(w));
+      for (uint32_t j = 0; j < m; j++) {
+        u64 wc[4];
+        fr.from_mont(wc, w);
+        Jac<N> t, neg_t, lo = a[k + j];
+        jac_scalar_mul<N>(cv, t, a[k + j + m], wc, 4);
+        neg_t = t;
+        cv.fq.neg(neg_t.y, t.y);
+        cv.add(a[k + j + m], lo, neg_t);
+        cv.add(a[k + j], lo, t);
+        fr.mul(w, w, w_m);
+      }
+    }
+    m *= 2;
+  }
+}
+
 template <int N> static int get_constant(const Curve<N>& c, int which, void* out) {
   switch (which) {
     case 0: memcpy(out, c.fq.p, 8 * N); return 0;
@@ -833,5 +891,29 @@ int oracle_gen_points(int curve, uint64_t seed, size_t start, size_t n, int nthr
 }
 
 unsigned oracle_window_for(size_t n) { return window_for(n); }
+
+// In-place FFT over G1 points (Jacobian, Montgomery); omega_mont: primitive 2^log_n-th root of unity
+// in Fr, Montgomery form (arkworks' in-memory layout).  ec-gpu-proxy/src/ec_fft_cpu.rs:12-57.
+int oracle_ec_fft(int curve, void* jac_inout, uint32_t log_n, const void* omega_mont) {
+  DISPATCH(curve, ec_fft_serial<4>(g_bn254, g_bn254_fr, (Jac<4>*)jac_inout, log_n, (const u64*)omega_mont),
+           ec_fft_serial<6>(g_bls381, g_bls381_fr, (Jac<6>*)jac_inout, log_n, (const u64*)omega_mont));
+  return 0;
+}
+// Fr helpers for tests: op 0 = to Montgomery form, 1 = from Montgomery form, 2 = multiply (Montgomery)
+int oracle_fr_op(int curve, int op, const void* a, const void* b, void* out, size_t count) {
+  init_curves();
+  const Field<4>& fr = curve == 0 ? g_bn254_fr : g_bls381_fr;
+  if (curve != 0 && curve != 1) return -100;
+  const u64* pa = (const u64*)a;
+  const u64* pb = (const u64*)b;
+  u64* po = (u64*)out;
+  for (size_t i = 0; i < count; i++, pa += 4, po += 4) {
+    if (op == 0) fr.to_mont(po, pa);
+    else if (op == 1) fr.from_mont(po, pa);
+    else if (op == 2) { fr.mul(po, pa, pb); pb += 4; }
+    else return -1;
+  }
+  return 0;
+}
 
 }  // extern "C"

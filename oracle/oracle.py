@@ -48,6 +48,8 @@ def lib():
         _lib.oracle_scalar_mul.argtypes = [i32, vp, vp, vp]
         _lib.oracle_gen_scalars.argtypes = [i32, u64, sz, sz, vp]
         _lib.oracle_gen_points.argtypes = [i32, u64, sz, sz, i32, vp]
+        _lib.oracle_ec_fft.argtypes = [i32, vp, u32, vp]
+        _lib.oracle_fr_op.argtypes = [i32, i32, vp, vp, vp, sz]
         _lib.oracle_window_for.argtypes = [sz]
         _lib.oracle_window_for.restype = ctypes.c_uint
     return _lib
@@ -169,6 +171,28 @@ def gen_scalars(curve, seed, n, start=0):
 def gen_points(curve, seed, n, start=0, nthreads=None):
     out = np.zeros((n, 2 * FQ_BYTES[curve]), dtype=np.uint8)
     rc = lib().oracle_gen_points(curve, seed, start, n, nthreads or ncores(), _ptr(out))
+    assert rc == 0
+    return out
+
+
+def fr_op(curve, op, a, b=None):
+    """Scalar field: op 0 to Montgomery, 1 from Montgomery, 2 Montgomery product.  [count, 32] uint8."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.zeros_like(a)
+    rc = lib().oracle_fr_op(curve, op, _ptr(a), _ptr(bb), _ptr(out), a.size // 32)
+    assert rc == 0
+    return out
+
+
+def ec_fft(curve, jac, omega_mont):
+    """serial_ec_fft restated: returns the transformed copy of jac ([n, 3*FQ] uint8, n a power of two)."""
+    out = np.ascontiguousarray(jac, dtype=np.uint8).copy()
+    n = out.size // (3 * FQ_BYTES[curve])
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    om = np.ascontiguousarray(omega_mont, dtype=np.uint8)
+    rc = lib().oracle_ec_fft(curve, _ptr(out), log_n, _ptr(om))
     assert rc == 0
     return out
 

@@ -210,6 +210,39 @@ def test_window_table_path(engine, oracle, ws, curve, c):
     assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc, 8), "chunked after precompute")
 
 
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("lines,chunks,chunk_len", [(1, 16, 300), (3, 8, 512), (2, 64, 64)])
+def test_window_table_chunked_and_multiline(engine, oracle, ws, curve, lines, chunks, chunk_len):
+    """SURVEY.md section 8f row 1 (AMT / per-segment shapes, ag-cuda-ec/benches/{multiexp,amt}.rs): a table
+    built with msm_bases_precompute_chunked serves chunked and multi-line calls -- every task folds
+    its windows into one bucket set -- and gives the same group elements as the plain path and as
+    the oracle, on the adversarial input set (zero / one / r-1 scalars, identity bases, P and -P)."""
+    L = chunks * chunk_len
+    pts, sc = adversarial_inputs(oracle, curve, L * lines)
+    sc = sc[:L]
+    w = ws[curve]
+    bases_gpu = engine.upload_multiexp_bases(w, pts)
+    want = oracle.multiple_multiexp(curve, pts, sc, chunks)
+    plain = engine.multiple_multiexp(w, bases_gpu, sc, chunks, 8, True)
+    plain_c = w.timings()["window_bits"]
+    assert_same_points(oracle, curve, plain, want, "plain")
+    tc = bases_gpu.precompute_chunked(chunk_len)
+    assert 8 <= tc <= 24
+    folded = engine.multiple_multiexp(w, bases_gpu, sc, chunks, 8, True)
+    t = w.timings()
+    assert t["window_bits"] == tc and tc > plain_c, (tc, plain_c)
+    assert folded.shape[0] == lines * chunks
+    assert_same_points(oracle, curve, folded, want, "folded chunked")
+    # a different chunking of the same row on the same table (cost model decides; result unchanged)
+    got = engine.multiple_multiexp(w, bases_gpu, sc, chunks // 2, 8, True)
+    assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc, chunks // 2), "other chunking")
+    # a shorter scalar row: more lines are inferred (points / L), table stride stays the shard size
+    L2 = L // 2
+    got = engine.multiple_multiexp(w, bases_gpu, sc[:L2], chunks // 2, 8, True)
+    assert got.shape[0] == (L * lines // L2) * (chunks // 2)
+    assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc[:L2], chunks // 2), "short row")
+
+
 def test_window_table_sharded_resident(engine, oracle):
     """MultiexpKernel with resident sharded bases + tables (one device here; N devices in bench)."""
     lib = engine.load_library()

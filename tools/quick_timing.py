@@ -40,6 +40,10 @@ def main():
             t2 = time.time()
             assert lib.msm_bases_precompute(h, bh, pre) == 0, lib.msm_last_error(h)
             print("precompute: c=%d in %.3f s" % (lib.msm_bases_table_window(bh), time.time() - t2))
+        if os.environ.get("PRECOMPUTE_CHUNKED"):
+            t2 = time.time()
+            assert lib.msm_bases_precompute_chunked(h, bh, L // chunks) == 0, lib.msm_last_error(h)
+            print("precompute_chunked(%d): c=%d in %.3f s" % (L // chunks, lib.msm_bases_table_window(bh), time.time() - t2))
         for c in windows:
             ws.set_window_bits(c)
             best = None
