@@ -424,6 +424,27 @@ template <class F> MSM_D bool load_base(const PackedAffine<F>* p, Affine<F>& out
   return any != 0;
 }
 
+// The same in two steps, so that the raw words of the NEXT point can be in flight during a mixed add.
+template <class F> MSM_D void load_base_words(const PackedAffine<F>* p, uint32_t* w) {
+  constexpr int WORDS = 2 * F::PACKED_WORDS;
+  static_assert(WORDS % 4 == 0, "packed point must be a multiple of 16 bytes");
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int j = 0; j < WORDS / 4; j++) {
+    uint4 t = __ldg(q + j);
+    w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+  }
+}
+template <class F> MSM_D bool unpack_base(const uint32_t* w, Affine<F>& out) {
+  constexpr int WORDS = 2 * F::PACKED_WORDS;
+  uint32_t any = 0;
+#pragma unroll
+  for (int j = 0; j < WORDS; j++) any |= w[j];
+  out.x = F::unpack(w);
+  out.y = F::unpack(w + F::PACKED_WORDS);
+  return any != 0;
+}
+
 // largest g in [0, NB) with bucket_start[g] <= pos  (pos < bucket_start[NB])
 MSM_D uint32_t find_bucket(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t pos) {
   uint32_t lo = 0, hi = NB;  // invariant: bucket_start[lo] <= pos < bucket_start[hi]
@@ -461,6 +482,14 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
   bool started_before = __ldg(bucket_start + g) < s;
   Xyzz<F> acc = xyzz_inf<F>();
 
+  // The point of entry pos+1 is fetched (raw words, 128-bit loads) before the mixed addition of
+  // entry pos starts, and the entry index one further ahead: the two dependent loads of the gather
+  // are off the critical path of the IMAD chains.
+  constexpr int WORDS = 2 * F::PACKED_WORDS;
+  uint32_t nxt[WORDS];
+  uint32_t ent = __ldg(entries + s);
+  load_base_words<F>(bases + (ent & 0x7fffffffu), nxt);
+  uint32_t ent_ahead = s + 1 < e ? __ldg(entries + s + 1) : ent;
   for (uint32_t pos = s; pos < e; pos++) {
     if (pos == gend) {
       // bucket g is complete: flush and move to the next non-empty bucket
@@ -472,10 +501,16 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
         gend = __ldg(bucket_start + g + 1);
       } while (gend == pos);
     }
-    const uint32_t ent = __ldg(entries + pos);
     Affine<F> pt;
-    if (load_base<F>(bases + (ent & 0x7fffffffu), pt)) {
-      pt = aff_cneg<F>(pt, (ent >> 31) != 0);
+    const bool finite = unpack_base<F>(nxt, pt);
+    const bool negate = (ent >> 31) != 0;
+    ent = ent_ahead;
+    if (pos + 1 < e) {
+      load_base_words<F>(bases + (ent & 0x7fffffffu), nxt);
+      if (pos + 2 < e) ent_ahead = __ldg(entries + pos + 2);
+    }
+    if (finite) {
+      pt = aff_cneg<F>(pt, negate);
       xyzz_madd<F>(acc, pt);
     }
   }
