@@ -71,8 +71,9 @@ inline uint32_t choose_table_window(uint32_t chunk_len, uint32_t bits, uint64_t 
 struct Plan {
   Geometry geo;
   uint32_t n_lines, S, n_slices, Q, RW, PG, n_tasks;
+  uint32_t slices_cap;  // upper bound of the slices of one sub-batch
   uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
-  uint32_t n_sub;   // sub-batches of a pipelined single-task call (each fills its own bucket array)
+  uint32_t n_sub;   // sub-batches of a pipelined single-task call (they continue one shared bucket array)
   mutable uint32_t scatter_passes = 1;  // filled in by enqueue_msm (0: two-level partition scatter)
   bool partition;   // large calls: two-level scatter through a (bucket id, entry) temporary
   uint64_t E_max;
@@ -112,11 +113,12 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   pl.E_max = (uint64_t)g.L * g.W;
   if (pl.E_max >= (1ull << 31) || (uint64_t)L * n_lines >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
   // slice length: enough slices to fill the machine several times over, few cut buckets
-  uint32_t S = (uint32_t)(pl.E_max / (148ull * 512 * 8));
+  uint32_t S = (uint32_t)(pl.E_max / n_sub / (148ull * 512 * 8));
   if (const char* env = getenv("MSM_B200_SLICE")) S = (uint32_t)atoi(env);
   S = S < 8 ? 8 : (S > 1024 ? 1024 : S);
   pl.S = S;
   pl.n_slices = (uint32_t)((pl.E_max + S - 1) / S);
+  pl.slices_cap = pl.n_slices / n_sub + g.W / S + 3;
   // buckets per reduction thread: the per-thread fix-up (first_weight * plain sum, a ~c-bit
   // double-and-add) is amortised over Q buckets; keep about one wave of threads on the machine
   {
@@ -132,26 +134,29 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   pl.PG = TG / pl.RW;
   const uint32_t n_tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
   size_t b = 0;
-  // per sub-batch (n_sub == 1: the whole call); sizes are upper bounds for every sub-batch
-  b += n_sub * Arena::padded((size_t)(g.NB + 1) * 4) * 3;                    // counts, bucket_start, cursor
-  b += n_sub * Arena::padded((size_t)(n_tiles + 1) * 4);                     // tile sums + grand total
-  b += n_sub * Arena::padded((pl.E_max / n_sub + g.W) * 4);                  // entries
+  // the sub-batches of a pipelined call run one after the other on the stream and share this scratch;
+  // sizes are upper bounds for every sub-batch (n_sub == 1: the whole call)
+  b += Arena::padded((size_t)(g.NB + 1) * 4) * 3;                            // counts, bucket_start, cursor
+  b += Arena::padded((size_t)(n_tiles + 1) * 4);                             // tile sums + grand total
+  b += Arena::padded((pl.E_max / n_sub + g.W) * 4);                          // entries
   // measured slower than the bucket-range passes on B200 (2^24, c = 22: 6.8 vs 5.2 ms): off unless asked for
   pl.partition = false;
   if (const char* env = getenv("MSM_B200_PARTITION")) pl.partition = atoi(env) != 0;
-  if (pl.partition) b += n_sub * (2 * Arena::padded((pl.E_max / n_sub + g.W) * 4) + Arena::padded(4096 * 4));  // tmp_g, tmp_v, bin cursors
-  b += n_sub * Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));      // bucket accumulators
-  b += n_sub * Arena::padded((size_t)2 * (pl.n_slices / n_sub + 2) * n_lines * sizeof(Xyzz<F>));  // slice partials
+  if (pl.partition) b += (2 * Arena::padded((pl.E_max / n_sub + g.W) * 4) + Arena::padded(4096 * 4));  // tmp_g, tmp_v, bin cursors
+  b += Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));              // bucket accumulators (shared by the sub-batches)
+  b += Arena::padded((size_t)2 * pl.slices_cap * n_lines * sizeof(Xyzz<F>));  // slice partials
   b += 2 * Arena::padded((size_t)pl.n_tasks * pl.W_sets * pl.PG * sizeof(Xyzz<F>));  // group partials (ping-pong)
-  b += n_sub * Arena::padded((size_t)(n_lines + (size_t)n_lines * (pl.n_slices / HEAVY_SPAN + 1)) * 4);  // heavy-bucket work list
+  b += Arena::padded(((size_t)2 * n_lines + (size_t)n_lines * (pl.n_slices / HEAVY_SPAN + 1) +
+                      (size_t)n_lines * pl.slices_cap) * 4);  // cut-bucket and heavy-bucket work lists
   pl.scratch_bytes = b;
   return MSM_OK;
 }
 
 // Enqueue one whole MSM batch on dc.stream.  d_scalars / d_out are device pointers.  No sync.
 // pl.n_sub > 1 (single-task calls only): the scalar row is processed in n_sub contiguous
-// sub-batches, each sorted and accumulated into its own bucket array as soon as sub_ready[k] has
-// fired (its scalars have arrived from the host); the reduction sums the arrays.
+// sub-batches, each sorted and accumulated as soon as sub_ready[k] has fired (its scalars have
+// arrived from the host); sub-batch k > 0 continues the buckets sub-batch k-1 left (carry_in), so
+// the per-bucket work of the reduction is done once.
 template <class F>
 int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<F>* d_bases,
                 uint32_t line_stride, const uint32_t* d_scalars, ApiJacobian<F>* d_out, bool timed,
@@ -162,13 +167,15 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
   const uint32_t n_sub = pl.n_sub;
   const uint32_t tb = 128;
   cudaStream_t st = dc.stream;
-  Xyzz<F>* bucket_acc = dc.arena.take<Xyzz<F>>((size_t)g.NB * pl.n_lines * n_sub);
+  Xyzz<F>* bucket_acc = dc.arena.take<Xyzz<F>>((size_t)g.NB * pl.n_lines);
   Xyzz<F>* group_partials = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
   Xyzz<F>* group_partials2 = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
 
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
   const uint32_t L_sub = (g.L + n_sub - 1) / n_sub;
+  const size_t arena_mark = dc.arena.off;
   for (uint32_t sb = 0; sb < n_sub; sb++) {
+    dc.arena.off = arena_mark;  // sub-batches are stream-ordered: they reuse the same scratch
     Geometry sg = g;
     uint32_t S = pl.S, n_slices = pl.n_slices;
     uint64_t E_max = pl.E_max;
@@ -186,11 +193,16 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     uint32_t* cursor = dc.arena.take<uint32_t>(g.NB + 1);
     uint32_t* tile_sums = dc.arena.take<uint32_t>(n_tiles + 1);
     uint32_t* entries = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
-    Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * (pl.n_slices / n_sub + 2) * pl.n_lines);
+    Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * pl.slices_cap * pl.n_lines);
     const uint32_t heavy_cap = n_slices / HEAVY_SPAN + 1;
-    uint32_t* heavy_count = dc.arena.take<uint32_t>(pl.n_lines + (size_t)pl.n_lines * (pl.n_slices / HEAVY_SPAN + 1));
+    // [cut_count | heavy_count | heavy_list | cut_list]
+    uint32_t* cut_count = dc.arena.take<uint32_t>((size_t)2 * pl.n_lines + (size_t)pl.n_lines * (pl.n_slices / HEAVY_SPAN + 1) +
+                                                  (size_t)pl.n_lines * pl.slices_cap);
+    uint32_t* heavy_count = cut_count + pl.n_lines;
     uint32_t* heavy_list = heavy_count + pl.n_lines;
-    Xyzz<F>* acc_sb = bucket_acc + (size_t)sb * g.NB * pl.n_lines;
+    uint32_t* cut_list = heavy_list + (size_t)pl.n_lines * (pl.n_slices / HEAVY_SPAN + 1);
+    Xyzz<F>* acc_sb = bucket_acc;  // every sub-batch continues the same buckets (carry_in)
+    const uint32_t carry_in = sb > 0 ? 1u : 0u;
     const uint32_t* sc_sb = d_scalars + (size_t)first * 8;
     const PackedAffine<F>* bases_sb = (n_sub > 1 && !g.fold) ? d_bases + first : d_bases;
 
@@ -244,13 +256,16 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     if (aborted(ctx)) return MSM_ERR_ABORTED;
     // --- accumulate
     dim3 grid((n_slices + tb - 1) / tb, pl.n_lines);
+    // cut_count[n_lines] and heavy_count[n_lines] are adjacent: one memset
+    CU_TRY(ctx, cudaMemsetAsync(cut_count, 0, (size_t)2 * pl.n_lines * 4, st));
+    if (!carry_in) CU_TRY(ctx, cudaMemsetAsync(acc_sb, 0, (size_t)g.NB * pl.n_lines * sizeof(Xyzz<F>), st));  // all infinity
     k_accumulate<F><<<grid, tb, 0, st>>>(bases_sb, line_stride, entries, bucket_start, g.NB, bucket_start + g.NB,
-                                         S, n_slices, acc_sb, partials);
-    dim3 fgrid((g.NB + tb - 1) / tb, pl.n_lines);
-    CU_TRY(ctx, cudaMemsetAsync(heavy_count, 0, (size_t)pl.n_lines * 4, st));
-    k_fixup<F><<<fgrid, tb, 0, st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials, heavy_count, heavy_list,
-                                     heavy_cap);
-    dim3 hgrid(heavy_cap < 296 ? heavy_cap : 296, pl.n_lines);
+                                         S, n_slices, acc_sb, partials, carry_in, cut_count, cut_list);
+    // at most one cut bucket per slice
+    k_fixup_cut<F><<<grid, tb, 0, st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials, cut_count, cut_list,
+                                        heavy_count, heavy_list, heavy_cap);
+    const uint32_t hblocks = (heavy_cap + 3) / 4;
+    dim3 hgrid(hblocks < 148 * 8 ? hblocks : 148 * 8, pl.n_lines);
     k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials,
                                                              heavy_count, heavy_list, heavy_cap);
     dc.launches += 8;
@@ -261,7 +276,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
   {
     const uint64_t n_threads = (uint64_t)g.NB * pl.n_lines / pl.Q;
     k_bucket_reduce<F><<<(uint32_t)((n_threads + tb - 1) / tb), tb, tb * sizeof(Xyzz<F>), st>>>(
-        bucket_acc, (uint32_t)n_threads, g.B, pl.Q, pl.RW, group_partials, n_sub, (size_t)g.NB * pl.n_lines);
+        bucket_acc, (uint32_t)n_threads, g.B, pl.Q, pl.RW, group_partials);
     const uint32_t Ws = pl.W_sets;
     // the PG partials of every (task, window) group shrink 1024-fold per pass
     uint32_t pg = pl.PG;
@@ -339,12 +354,12 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   // previous chunk is already being sorted and accumulated (the 32 B/scalar upload is ~20 % of the
   // call otherwise).
   uint32_t n_sub = 1;
-  // Measured at 2^24 with the c = 22 table: 2 sub-batches 47.3 ms end to end, 1: 48.8, 4: 50.1, 8: 57.1 --
-  // every sub-batch repeats the per-bucket work, so only the coarsest split pays.
-  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 23)) n_sub = 2;
+  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 22)) n_sub = L >= (1u << 23) ? 8 : 4;
   if (const char* env = getenv("MSM_B200_PIPELINE")) {
     const int v = atoi(env);
-    if (v >= 1 && v <= 8 && !device_io && num_chunks == 1 && n_lines == 1) n_sub = (uint32_t)v;
+    // MSM_B200_PIPELINE_DEVICE: also split device-resident rows (measurement of the split's own cost)
+    if (v >= 1 && v <= 8 && (!device_io || getenv("MSM_B200_PIPELINE_DEVICE")) && num_chunks == 1 && n_lines == 1)
+      n_sub = (uint32_t)v;
   }
   Plan pl;
   int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0, n_sub,

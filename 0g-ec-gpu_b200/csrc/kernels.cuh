@@ -9,7 +9,7 @@
 //   k_accumulate      one thread per fixed-size slice of the sorted entry list; XYZZ mixed adds;
 //                     whole buckets are written directly, buckets cut by a slice boundary go to
 //                     per-slice partial slots
-//   k_fixup           combines the partial slots of cut buckets, writes infinity to empty buckets
+//   k_fixup_cut       combines the partial slots of the buckets cut by slice boundaries (listed by k_accumulate)
 //   k_bucket_reduce   running-sum reduction  sum_b b*S_b  split over threads + shared-memory tree
 //   k_window_combine  sums the per-window partials, Horner over windows, XYZZ -> Jacobian
 //
@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(128, (F::N <= 9 ? 4 : 3))
 k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
              const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start,
              uint32_t NB, const uint32_t* __restrict__ E_ptr, uint32_t S, uint32_t n_slices,
-             Xyzz<F>* __restrict__ bucket_acc, Xyzz<F>* __restrict__ partials) {
+             Xyzz<F>* __restrict__ bucket_acc, Xyzz<F>* __restrict__ partials, uint32_t carry_in,
+             uint32_t* __restrict__ cut_count, uint32_t* __restrict__ cut_list) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t E = __ldg(E_ptr);  // = bucket_start[NB], number of non-zero digits
   if (t >= n_slices || (uint64_t)t * S >= E) return;
@@ -480,7 +481,9 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
   uint32_t g = find_bucket(bucket_start, NB, s);
   uint32_t gend = __ldg(bucket_start + g + 1);
   bool started_before = __ldg(bucket_start + g) < s;
-  Xyzz<F> acc = xyzz_inf<F>();
+  // carry_in (sub-batches after the first of a pipelined call): a bucket continues from the value the
+  // earlier sub-batches left in bucket_acc; only the thread that owns the bucket's first entry reads it
+  Xyzz<F> acc = (carry_in && !started_before) ? load_vec(&bucket_acc[g]) : xyzz_inf<F>();
 
   // The point of entry pos+1 is fetched (raw words, 128-bit loads) before the mixed addition of
   // entry pos starts, and the entry index one further ahead: the two dependent loads of the gather
@@ -494,12 +497,12 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
     if (pos == gend) {
       // bucket g is complete: flush and move to the next non-empty bucket
       store_vec(started_before ? &partials[2 * t] : &bucket_acc[g], acc);
-      acc = xyzz_inf<F>();
       started_before = false;
       do {
         g++;
         gend = __ldg(bucket_start + g + 1);
       } while (gend == pos);
+      acc = carry_in ? load_vec(&bucket_acc[g]) : xyzz_inf<F>();
     }
     Affine<F> pt;
     const bool finite = unpack_base<F>(nxt, pt);
@@ -518,6 +521,8 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
     store_vec(started_before ? &partials[2 * t] : &bucket_acc[g], acc);
   } else {
     store_vec(started_before ? &partials[2 * t] : &partials[2 * t + 1], acc);
+    // bucket g starts in this slice and continues in the next one(s): exactly one thread sees that
+    if (!started_before) cut_list[(size_t)line * n_slices + atomicAdd(&cut_count[line], 1u)] = g;
   }
 }
 
@@ -535,27 +540,26 @@ template <class F> MSM_D Xyzz<F> block_sum_xyzz(Xyzz<F> v, Xyzz<F>* sh) {
   return v;
 }
 
-// One thread per bucket: empty -> infinity; cut by slice boundaries -> sum of its partial slots.
-// Buckets spread over more than HEAVY_SPAN slices (skewed scalars; the short top window of a
-// folded table) go to a work list that k_fixup_heavy reduces with one block each.
+// Buckets cut by slice boundaries: one thread per entry of the list k_accumulate appended to sums
+// the bucket's partial slots (dense: every lane of a warp has the same work, unlike a
+// thread-per-bucket sweep where ~30 % of the lanes take this branch).  Empty buckets need no
+// visit: the bucket array is zero-filled (= infinity) before the first sub-batch.  Buckets spread
+// over more than HEAVY_SPAN slices (skewed scalars; the short top window of a folded table) go to
+// a second list that k_fixup_heavy reduces with one warp each.
 constexpr uint32_t HEAVY_SPAN = 16;
 template <class F>
 __global__ void __launch_bounds__(128)
-k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
-        Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials,
-        uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list, uint32_t heavy_cap) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= NB) return;
+k_fixup_cut(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
+            Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials,
+            const uint32_t* __restrict__ cut_count, const uint32_t* __restrict__ cut_list,
+            uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list, uint32_t heavy_cap) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t line = blockIdx.y;
+  if (i >= cut_count[line]) return;
   bucket_acc += (size_t)line * NB;
   partials += (size_t)line * 2 * n_slices;
-  const uint32_t start = bucket_start[g], end = bucket_start[g + 1];
-  if (start == end) {
-    store_vec(&bucket_acc[g], xyzz_inf<F>());
-    return;
-  }
-  const uint32_t t0 = start / S, t1 = (end - 1) / S;
-  if (t0 == t1) return;  // written directly by k_accumulate
+  const uint32_t g = cut_list[(size_t)line * n_slices + i];
+  const uint32_t t0 = bucket_start[g] / S, t1 = (bucket_start[g + 1] - 1) / S;
   if (t1 - t0 > HEAVY_SPAN) {
     const uint32_t slot = atomicAdd(&heavy_count[line], 1u);
     if (slot < heavy_cap) heavy_list[(size_t)line * heavy_cap + slot] = g;  // cap = n_slices/HEAVY_SPAN + 1 cannot overflow
@@ -566,27 +570,36 @@ k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint
   store_vec(&bucket_acc[g], acc);
 }
 
+// One warp per heavy bucket: lane-strided partial sums, then a 5-level tree through shared memory.
 template <class F>
 __global__ void __launch_bounds__(128)
 k_fixup_heavy(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
               Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials,
               const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list, uint32_t heavy_cap) {
   extern __shared__ uint4 smem_raw[];
-  Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw);
-  const uint32_t line = blockIdx.y;
+  Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw) + (threadIdx.x & ~31u);
+  const uint32_t line = blockIdx.y, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   bucket_acc += (size_t)line * NB;
   partials += (size_t)line * 2 * n_slices;
   const uint32_t count = min(heavy_count[line], heavy_cap);
-  for (uint32_t item = blockIdx.x; item < count; item += gridDim.x) {
+  for (uint32_t item = blockIdx.x * warps + (threadIdx.x >> 5); item < count; item += gridDim.x * warps) {
     const uint32_t g = heavy_list[(size_t)line * heavy_cap + item];
     const uint32_t t0 = bucket_start[g] / S, t1 = (bucket_start[g + 1] - 1) / S;
     // element 0 = slot 2*t0+1, element k = slot 2*(t0+k), k = 1 .. t1-t0
     Xyzz<F> acc = xyzz_inf<F>();
-    for (uint32_t k = threadIdx.x; k <= t1 - t0; k += blockDim.x)
+    for (uint32_t k = lane; k <= t1 - t0; k += 32)
       acc = xyzz_add<F>(acc, load_vec(k == 0 ? &partials[2 * t0 + 1] : &partials[2 * (t0 + k)]));
-    acc = block_sum_xyzz<F>(acc, sh);
-    if (threadIdx.x == 0) store_vec(&bucket_acc[g], acc);
-    __syncthreads();
+    sh[lane] = acc;
+    __syncwarp();
+    for (uint32_t stride = 16; stride >= 1; stride >>= 1) {
+      if (lane < stride) {
+        acc = xyzz_add<F>(acc, sh[lane + stride]);
+        sh[lane] = acc;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) store_vec(&bucket_acc[g], acc);
+    __syncwarp();
   }
 }
 
@@ -613,7 +626,7 @@ k_reduce_points(const Xyzz<F>* __restrict__ in, uint32_t count, uint32_t out_cou
 template <class F>
 __global__ void __launch_bounds__(128)
 k_bucket_reduce(const Xyzz<F>* __restrict__ bucket_acc, uint32_t n_threads, uint32_t B, uint32_t Q,
-                uint32_t RW, Xyzz<F>* __restrict__ out, uint32_t n_arrays, size_t array_stride) {
+                uint32_t RW, Xyzz<F>* __restrict__ out) {
   extern __shared__ uint4 smem_raw[];
   Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -623,8 +636,7 @@ k_bucket_reduce(const Xyzz<F>* __restrict__ bucket_acc, uint32_t n_threads, uint
     const uint32_t b0 = (uint32_t)(f % B);  // weight of bucket f+k is b0 + k + 1
     Xyzz<F> run = xyzz_inf<F>();
     for (int k = (int)Q - 1; k >= 0; k--) {
-      // sub-batches of a pipelined call each filled their own copy of the bucket array
-      for (uint32_t a = 0; a < n_arrays; a++) run = xyzz_add<F>(run, load_vec(&bucket_acc[a * array_stride + f + k]));
+      run = xyzz_add<F>(run, load_vec(&bucket_acc[f + k]));
       res = xyzz_add<F>(res, run);
     }
     if (b0) res = xyzz_add<F>(res, xyzz_mul_small<F>(run, b0));

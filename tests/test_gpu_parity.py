@@ -243,6 +243,31 @@ def test_window_table_chunked_and_multiline(engine, oracle, ws, curve, lines, ch
     assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc[:L2], chunks // 2), "short row")
 
 
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("n_sub,table_c", [(2, 0), (3, 12), (8, 0), (8, 14), (5, 9)])
+def test_pipelined_sub_batches(engine, oracle, ws, curve, n_sub, table_c, monkeypatch):
+    """Host scalars of a single-task call are uploaded and processed in sub-batches that continue
+    one shared bucket array (carry_in): same group element for any split, with and without a
+    window table, on the adversarial set (so that buckets receive entries from several sub-batches,
+    cancel to infinity in between, and stay empty in some sub-batches)."""
+    monkeypatch.setenv("MSM_B200_PIPELINE", str(n_sub))
+    n = 5003  # not a multiple of the split
+    pts, sc = adversarial_inputs(oracle, curve, n)
+    w = ws[curve]
+    bases_gpu = engine.upload_multiexp_bases(w, pts)
+    if table_c >= 11:
+        bases_gpu.precompute(table_c)
+    elif table_c:
+        w.set_window_bits(table_c)
+    try:
+        got = engine.multiple_multiexp(w, bases_gpu, sc, 1, 8, True)
+        t = w.timings()
+    finally:
+        w.set_window_bits(0)
+    assert t["sub_batches"] == n_sub
+    assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc, 1), f"pipeline {n_sub}")
+
+
 def test_window_table_sharded_resident(engine, oracle):
     """MultiexpKernel with resident sharded bases + tables (one device here; N devices in bench)."""
     lib = engine.load_library()
