@@ -9,6 +9,7 @@ Contents:
   _lib.py        ctypes binding of include/msm_b200.h (fails loudly when the library is missing)
   multiexp.py    mirror of ag_cuda_ec::multiexp (upload_multiexp_bases_*, multiple_multiexp_*)
   kernel.py      mirror of ec_gpu_proxy::multiexp::MultiexpKernel
+  ec_fft.py      mirror of ag_cuda_ec::ec_fft (radix_ec_fft_*)
 """
 from ._lib import (  # noqa: F401
     BLS12_381_G1,
@@ -37,4 +38,5 @@ from .multiexp import (  # noqa: F401
     upload_multiexp_bases_st,
 )
 from .kernel import MultiexpKernel, Worker  # noqa: F401
+from .ec_fft import radix_ec_fft, radix_ec_fft_mt, radix_ec_fft_st  # noqa: F401
 from .sharding import chunk_size, shard_range  # noqa: F401

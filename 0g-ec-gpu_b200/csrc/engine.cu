@@ -384,6 +384,19 @@ int msm_multiple_multiexp_montgomery(msm_ctx* ctx, const msm_bases* bases, const
   return rc;
 }
 
+int msm_ec_fft(msm_ctx* ctx, void* jacobian_inout, uint32_t log_n, const void* omegas_mont, uint32_t n_omegas) {
+  if (!ctx || !omegas_mont || (!jacobian_inout && log_n)) return MSM_ERR_INVALID;
+  LOCK_OR_BUSY(ctx);
+  if (aborted(ctx)) return MSM_ERR_ABORTED;
+  return ctx->ops->ec_fft(ctx, jacobian_inout, log_n, omegas_mont, n_omegas, false);
+}
+int msm_ec_fft_device(msm_ctx* ctx, void* d_jacobian_inout, uint32_t log_n, const void* omegas_mont, uint32_t n_omegas) {
+  if (!ctx || !omegas_mont || (!d_jacobian_inout && log_n)) return MSM_ERR_INVALID;
+  LOCK_OR_BUSY(ctx);
+  if (aborted(ctx)) return MSM_ERR_ABORTED;
+  return ctx->ops->ec_fft(ctx, d_jacobian_inout, log_n, omegas_mont, n_omegas, true);
+}
+
 int msm_test_fq_op(msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
   if (!ctx || !a || !out || op < 0 || op > 8) return MSM_ERR_INVALID;
   if (count == 0) return MSM_OK;

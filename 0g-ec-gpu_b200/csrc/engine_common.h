@@ -132,6 +132,7 @@ struct FieldOps {
   int (*test_ec)(msm_ctx*, int op, const void* a, const void* b, void* out, size_t count);
   int (*to_affine)(msm_ctx*, const void* jac, size_t count, int mont_out, void* out_xy, uint8_t* out_inf);
   int (*sum_points)(msm_ctx*, const void* d_in, size_t count, void* d_out);
+  int (*ec_fft)(msm_ctx*, void* jac, uint32_t log_n, const void* omegas_mont, uint32_t n_omegas, bool device_io);
 };
 const FieldOps* field_ops_bn254_u29();
 const FieldOps* field_ops_bn254_sat();

@@ -11,6 +11,7 @@
 
 #include "engine_common.h"
 #include "kernels.cuh"
+#include "ecfft.cuh"
 
 namespace msm {
 
@@ -738,6 +739,58 @@ template <class F> int sum_points_impl(msm_ctx* ctx, const void* d_in, size_t co
   return MSM_OK;
 }
 
+// radix_ec_fft (ag-cuda-ec/src/ec_fft.rs:13-99): in-place DFT of 2^log_n Jacobian points.
+// device_io: jac is a device pointer on device 0 (omegas are always a small host array).
+template <class F>
+int ec_fft_impl(msm_ctx* ctx, void* jac, uint32_t log_n, const void* omegas_mont, uint32_t n_omegas, bool device_io) {
+  using PR = typename std::conditional<F::API_WORDS == 8, Bn254Fr, Bls381Fr>::type;
+  if (log_n > 26 || n_omegas < log_n || n_omegas > 64) {
+    set_error(ctx, "ec_fft: need 2^log_n <= 2^26 points and omegas[i] = omega^(2^i) for i < log_n");
+    return MSM_ERR_INVALID;
+  }
+  if (log_n == 0) return MSM_OK;
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const uint32_t n = 1u << log_n;
+  const size_t jb = (size_t)n * sizeof(ApiJacobian<F>);
+  CU_TRY(ctx, dc.io.ensure((device_io ? 0 : Arena::padded(jb)) + Arena::padded((size_t)n_omegas * 32) +
+                           Arena::padded((size_t)(n / 2) * 32)));
+  ApiJacobian<F>* d_jac = device_io ? static_cast<ApiJacobian<F>*>(jac) : dc.io.take<ApiJacobian<F>>(n);
+  uint32_t* d_omegas = dc.io.take<uint32_t>((size_t)n_omegas * 8);
+  uint32_t* d_tw = dc.io.take<uint32_t>((size_t)(n / 2) * 8);
+  CU_TRY(ctx, dc.arena.ensure(Arena::padded((size_t)n * sizeof(Xyzz<F>))));
+  Xyzz<F>* x = dc.arena.take<Xyzz<F>>(n);
+  cudaStream_t st = dc.stream;
+  CU_TRY(ctx, cudaEventRecord(dc.ev[0], st));
+  if (!device_io) CU_TRY(ctx, cudaMemcpyAsync(d_jac, jac, jb, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, cudaMemcpyAsync(d_omegas, omegas_mont, (size_t)n_omegas * 32, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
+  k_fft_twiddles<PR><<<(n / 2 + 127) / 128, 128, 0, st>>>(d_omegas, n / 2, d_tw);
+  k_fft_load<F><<<(n + 127) / 128, 128, 0, st>>>(d_jac, log_n, x);
+  dc.launches += 2;
+  for (uint32_t s = 0; s < log_n; s++) {
+    if (aborted(ctx)) {  // SingleEcFftKernel polls maybe_abort once per round (ec-gpu-proxy/src/ec_fft.rs:104-108)
+      cudaStreamSynchronize(st);
+      return MSM_ERR_ABORTED;
+    }
+    const uint32_t m = 1u << s;
+    k_fft_round<F><<<(n / 2 + 63) / 64, 64, 0, st>>>(x, n, m, n / (2 * m), d_tw);
+    dc.launches += 1;
+  }
+  k_fft_store<F><<<(n + 127) / 128, 128, 0, st>>>(x, n, d_jac);
+  dc.launches += 1;
+  CU_TRY(ctx, cudaEventRecord(dc.ev[4], st));
+  CU_TRY(ctx, cudaGetLastError());
+  if (!device_io) CU_TRY(ctx, cudaMemcpyAsync(jac, d_jac, jb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  msm_timings& t = ctx->tm;
+  memset(&t, 0, sizeof(t));
+  cudaEventElapsedTime(&t.h2d_ms, dc.ev[0], dc.ev[1]);
+  cudaEventElapsedTime(&t.total_ms, dc.ev[1], dc.ev[4]);
+  t.kernel_launches = dc.launches;
+  return MSM_OK;
+}
+
 template <class F> FieldOps make_field_ops(const char* name) {
   FieldOps o;
   o.name = name;
@@ -752,6 +805,7 @@ template <class F> FieldOps make_field_ops(const char* name) {
   o.test_ec = &test_ec_impl<F>;
   o.to_affine = &to_affine_impl<F>;
   o.sum_points = &sum_points_impl<F>;
+  o.ec_fft = &ec_fft_impl<F>;
   return o;
 }
 

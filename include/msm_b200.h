@@ -169,6 +169,20 @@ int msm_multiexp(msm_ctx* ctx, const void* bases_xy_mont, const void* scalars, s
 int msm_multiexp_resident(msm_ctx* ctx, const msm_bases* bases, size_t skip, const void* scalars,
                           size_t n, void* out_jacobian);
 
+/* ---- EC-FFT ---------------------------------------------------- */
+/* radix_ec_fft (ag-cuda-ec/src/ec_fft.rs:13-99) / SingleEcFftKernel::radix_ec_fft
+ * (ec-gpu-proxy/src/ec_fft.rs:53-160): in-place discrete Fourier transform of n = 2^log_n G1
+ * points, out[k] = sum_j omega^(j k) in[j], natural order in and out -- what
+ * Radix2EvaluationDomain::fft returns (ag-cuda-ec/src/ec_fft.rs:131-137).  Points are Jacobian
+ * {x, y, z} Montgomery (Vec<Curve>), infinity <=> z == 0; omegas_mont[i] = omega^(2^i) in arkworks'
+ * in-memory Fr layout (4 x u64 little-endian, Montgomery form), n_omegas >= log_n entries (the
+ * reference passes 32, ag-cuda-ec/src/ec_fft.rs:120-124).  Passing the powers of omega^-1 gives
+ * the unscaled inverse transform (ag-cuda-ec/benches/ec_fft.rs:88-106).  Synchronous. */
+int msm_ec_fft(msm_ctx* ctx, void* jacobian_inout, uint32_t log_n, const void* omegas_mont, uint32_t n_omegas);
+/* Same with the point array in device memory of device 0 (omegas stay a host array). */
+int msm_ec_fft_device(msm_ctx* ctx, void* d_jacobian_inout, uint32_t log_n, const void* omegas_mont,
+                      uint32_t n_omegas);
+
 /* ---- small device-side helpers used by callers, tests and the bench ----------------------- */
 /* Sum `count` Jacobian points that live in device memory of device 0 into one Jacobian point
  * (device memory): the on-device replacement of the host loop acc.add_assign(&r)

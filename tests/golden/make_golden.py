@@ -9,7 +9,9 @@
                        FIELD_add/sub/mul/sqr/double/mont/unmont, POINT_add/add_mixed/double and the
                        POINT_multiexp kernel.  Needs /root/reference; the fixture travels instead.
 
-Run from the repo root:  python tests/golden/make_golden.py
+  ec_fft_vectors.json  from oracle/pyref.py: the DFT of G1 points evaluated by its definition.
+
+Run from the repo root:  python tests/golden/make_golden.py   (--only-ec-fft: just the last file)
 """
 import json
 import os
@@ -137,8 +139,50 @@ def make_ref_cl():
         json.dump(out, f, indent=1)
 
 
+def make_ec_fft():
+    """ec_fft_vectors.json: the DFT of G1 points by its definition, out[k] = sum_j omega^(j k) P_j, in
+    oracle/pyref.py's big-integer affine arithmetic (no FFT structure at all).  omega = g^((r-1)/n) with
+    g the multiplicative generator arkworks uses for Fr (5 for BN254, 7 for BLS12-381), so omega is
+    Scalar::get_root_of_unity(n) of ag-cuda-ec/src/ec_fft.rs:120."""
+    out = {"generator": "tests/golden/make_golden.py make_ec_fft (oracle/pyref.py, naive O(n^2) DFT)", "curves": {}}
+    for cv, g in ((P.BN254, 5), (P.BLS12_381, 7)):
+        cases = []
+        for log_n in (3, 4):
+            n = 1 << log_n
+            omega = pow(g, (cv.r - 1) // n, cv.r)
+            assert pow(omega, n, cv.r) == 1 and pow(omega, n // 2, cv.r) == cv.r - 1
+            pts = P.gen_points(cv, SEED + 3 + log_n, 0, n)
+            pts[3] = None                      # the identity as an input
+            pts[5] = pts[4]                    # equal neighbours: a butterfly hits the doubling branch
+            lam = {2: 7, 6: cv.p - 5}          # non-trivial Jacobian representatives (x l^2, y l^3, l)
+            jac = b""
+            for i, pt in enumerate(pts):
+                if pt is None:
+                    x, y, z = 0, 1, 0
+                else:
+                    l = lam.get(i, 1)
+                    x, y, z = pt[0] * l * l % cv.p, pt[1] * l * l * l % cv.p, l
+                jac += cv.fq_to_bytes(cv.to_mont(x)) + cv.fq_to_bytes(cv.to_mont(y)) + cv.fq_to_bytes(cv.to_mont(z))
+            R_fr = 1 << 256
+            omegas = b"".join((pow(omega, 1 << i, cv.r) * R_fr % cv.r).to_bytes(32, "little") for i in range(32))
+            res = []
+            for k in range(n):
+                acc = None
+                for j, pt in enumerate(pts):
+                    if pt is not None:
+                        acc = cv.add(acc, cv.mul(pow(omega, j * k % n, cv.r), pt))
+                res.append(None if acc is None else [hex(acc[0]), hex(acc[1])])
+            cases.append({"log_n": log_n, "omega": hex(omega), "omegas_mont": hx(omegas), "input_jacobian": hx(jac),
+                          "output_affine": res})
+        out["curves"][cv.name] = cases
+    with open(os.path.join(HERE, "ec_fft_vectors.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    make_pyref()
-    make_ref_cl()
-    for fn in ("pyref_vectors.json", "ref_cl_vectors.json"):
+    if "--only-ec-fft" not in sys.argv:
+        make_pyref()
+        make_ref_cl()
+    make_ec_fft()
+    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")

@@ -193,3 +193,36 @@ def test_against_reference_cl_live(oracle, curve):
     want = oracle.multiple_multiexp(curve, pts, sc, 32)
     for w, neg in ((4, True), (6, False)):
         assert_same_points(oracle, curve, ref_cl.multiple_multiexp(curve, pts, sc, 32, w, neg), want, f"w={w}")
+
+
+# ---------------------------------------------------------------------------------------------
+# EC-FFT: the oracle's restatement of serial_ec_fft
+# (ec-gpu-proxy/src/ec_fft_cpu.rs:12-57) against the transform's definition evaluated by pyref.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", [0, 1])
+def test_ec_fft_oracle_vs_naive_dft_golden(oracle, curve):
+    for case in _load("ec_fft_vectors.json")["curves"][NAMES[curve]]:
+        jac = _b(case["input_jacobian"], 3 * FQ[curve])
+        omegas = _b(case["omegas_mont"], 32)
+        assert jac.shape[0] == 1 << case["log_n"]
+        got = oracle.ec_fft(curve, jac, omegas[0])
+        assert _affine_ints(oracle, curve, got) == case["output_affine"], f"log_n={case['log_n']}"
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_ec_fft_oracle_inverse_round_trip(oracle, pyref, curve):
+    """FFT with omega, then with omega^-1, is n times the input (ag-cuda-ec/benches/ec_fft.rs:88-106)."""
+    cv = pyref.CURVES[curve]
+    log_n, g = 5, {0: 5, 1: 7}[curve]
+    n = 1 << log_n
+    omega = pow(g, (cv.r - 1) // n, cv.r)
+    mont = lambda v: np.frombuffer((v * (1 << 256) % cv.r).to_bytes(32, "little"), dtype=np.uint8)  # noqa: E731
+    pts = oracle.gen_points(curve, 99, n)
+    jac = np.zeros((n, 3 * FQ[curve]), dtype=np.uint8)
+    jac[:, :2 * FQ[curve]] = pts
+    jac[:, 2 * FQ[curve]:] = oracle.constant(curve, 1)
+    fwd = oracle.ec_fft(curve, jac, mont(omega))
+    back = oracle.ec_fft(curve, fwd, mont(pow(omega, -1, cv.r)))
+    want = np.stack([oracle.scalar_mul(curve, pts[i], np.frombuffer(n.to_bytes(32, "little"), dtype=np.uint8))
+                     for i in range(n)])
+    assert_same_points(oracle, curve, back, want, "ifft(fft(x)) == n x")
