@@ -76,7 +76,9 @@ struct Plan {
   uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
   uint32_t n_sub;   // sub-batches of a pipelined single-task call (they continue one shared bucket array)
   mutable uint32_t scatter_passes = 1;  // filled in by enqueue_msm (0: two-level partition scatter)
-  bool partition;   // large calls: two-level scatter through a (bucket id, entry) temporary
+  bool partition;   // two-level scatter through a (bucket id, entry) temporary, global cursor atomics (measured slower)
+  uint32_t sort_mode;  // 0: single-level atomic sort, 2: binned sort (shared-memory atomics)
+  uint32_t bin_shift;  // binned sort: low bucket-id bits sorted inside a bin
   uint64_t E_max;
   size_t scratch_bytes;
 };
@@ -143,6 +145,22 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   // measured slower than the bucket-range passes on B200 (2^24, c = 22: 6.8 vs 5.2 ms): off unless asked for
   pl.partition = false;
   if (const char* env = getenv("MSM_B200_PARTITION")) pl.partition = atoi(env) != 0;
+  // binned sort for large calls: at most 1024 bins of at most 8192 buckets
+  pl.sort_mode = 0;
+  pl.bin_shift = 0;
+  {
+    uint32_t nb_log = 0;
+    while ((1ull << nb_log) < g.NB) nb_log++;
+    const uint32_t shift = nb_log > 10 ? (nb_log - 10 < 11 ? 11 : nb_log - 10) : 11;
+    const bool fits = shift <= 13 && (((uint64_t)g.NB + (1ull << shift) - 1) >> shift) <= 1024;
+    bool want = pl.E_max / n_sub >= (1ull << 22);  // measured break-even against the single-level sort: ~2^21 digits
+    if (const char* env = getenv("MSM_B200_SORT")) want = strcmp(env, "binned") == 0;
+    if (want && fits && !pl.partition) {
+      pl.sort_mode = 2;
+      pl.bin_shift = shift;
+    }
+  }
+  if (pl.sort_mode == 2) b += 2 * Arena::padded((pl.E_max / n_sub + g.W) * 4) + 4 * Arena::padded(1025 * 4);
   if (pl.partition) b += (2 * Arena::padded((pl.E_max / n_sub + g.W) * 4) + Arena::padded(4096 * 4));  // tmp_g, tmp_v, bin cursors
   b += Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));              // bucket accumulators (shared by the sub-batches)
   b += Arena::padded((size_t)2 * pl.slices_cap * n_lines * sizeof(Xyzz<F>));  // slice partials
@@ -211,6 +229,37 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     // --- sort: histogram, scan, scatter
     CU_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.NB + 1) * 4, st));
     const uint32_t db = 256, dg = (sg.L + db - 1) / db;
+    if (pl.sort_mode == 2 && dg) {
+      // binned sort (kernels.cuh): every per-digit atomic in shared memory
+      uint32_t* tmp_g = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
+      uint32_t* tmp_v = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
+      uint32_t* bin_count = dc.arena.take<uint32_t>(1024);  // [bin_count | bin_cursor]: one memset
+      uint32_t* bin_cursor = dc.arena.take<uint32_t>(1024);
+      uint32_t* bin_start = dc.arena.take<uint32_t>(1025);
+      uint32_t* tile_start = dc.arena.take<uint32_t>(1025);
+      const uint32_t bin_shift = pl.bin_shift;
+      const uint32_t n_bins = (uint32_t)(((uint64_t)g.NB + (1ull << bin_shift) - 1) >> bin_shift);
+      CU_TRY(ctx, cudaMemsetAsync(bin_count, 0, (size_t)((char*)bin_start - (char*)bin_count), st));
+      launch_bin_count((sg.L + BIN_COUNT_SCALARS - 1) / BIN_COUNT_SCALARS, st, sc_sb, sg, bin_shift, n_bins, bin_count);
+      k_bin_scan<<<1, SCAN_BLOCK, 0, st>>>(bin_count, n_bins, bin_start, tile_start);
+      uint32_t tile = 12288 / g.W;
+      tile = tile > 1024 ? 1024 : (tile < 64 ? 64 : tile);
+      const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * g.W) * 4;
+      CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, sc_sb, sg, tile, bin_shift, n_bins, bin_start, 0u,
+                                   bin_cursor, tmp_g, tmp_v));
+      const uint32_t max_tiles = (uint32_t)(E_max / BIN_TILE) + n_bins + 1;
+      const size_t hsmem = (size_t)4 << bin_shift;
+      k_bin_hist<<<max_tiles, BIN_BLOCK, hsmem, st>>>(tmp_g, bin_start, tile_start, n_bins, bin_shift, g.NB, counts);
+      k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
+      k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
+      k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(bucket_start, g.NB, tile_sums, tile_sums + n_tiles, cursor);
+      const size_t psmem = bin_place_smem(bin_shift);
+      CU_TRY(ctx, cudaFuncSetAttribute(k_bin_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      k_bin_place<<<max_tiles, PLACE_BLOCK, psmem, st>>>(tmp_g, tmp_v, bin_start, tile_start, n_bins, bin_shift, g.NB,
+                                                        cursor, entries);
+      pl.scatter_passes = 0;
+      dc.launches += 5;
+    } else {
     if (dg) launch_digits<false>(dg, db, st, sc_sb, sg, counts, nullptr, 0u, g.NB);
     k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
     k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
@@ -233,7 +282,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
       const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * g.W) * 4;
       CU_TRY(ctx, cudaMemsetAsync(bin_cursor, 0, (size_t)n_bins * 4, st));
       CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, sc_sb, sg, tile, bin_shift, n_bins, bucket_start,
-                                   bin_cursor, tmp_g, tmp_v));
+                                   bin_shift, bin_cursor, tmp_g, tmp_v));
       k_final_scatter<<<(uint32_t)((E_max + 255) / 256), 256, 0, st>>>(tmp_g, tmp_v, bucket_start + g.NB, cursor, entries);
       pl.scatter_passes = 0;
       dc.launches += 2;
@@ -252,6 +301,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
         launch_digits<true>(dg, db, st, sc_sb, sg, cursor, entries, lo, hi);
         dc.launches += 1;
       }
+    }
     }
     if (timed && sb == 0) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
     if (aborted(ctx)) return MSM_ERR_ABORTED;

@@ -178,8 +178,8 @@ constexpr int SCAN_BLOCK = 256;
 constexpr int SCAN_ITEMS = 8;  // per thread
 constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t warp_sums[SCAN_BLOCK / 32];
+template <int BS> __device__ __forceinline__ uint32_t block_exclusive_scan_t(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[BS / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t x = v;
 #pragma unroll
@@ -190,19 +190,22 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
   if (lane == 31) warp_sums[wid] = x;
   __syncthreads();
   if (wid == 0) {
-    uint32_t s = lane < SCAN_BLOCK / 32 ? warp_sums[lane] : 0;
+    uint32_t s = lane < BS / 32 ? warp_sums[lane] : 0;
 #pragma unroll
-    for (int o = 1; o < SCAN_BLOCK / 32; o <<= 1) {
+    for (int o = 1; o < BS / 32; o <<= 1) {
       uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
       if (lane >= o) s += y;
     }
-    if (lane < SCAN_BLOCK / 32) warp_sums[lane] = s;
+    if (lane < BS / 32) warp_sums[lane] = s;
   }
   __syncthreads();
   const uint32_t warp_off = wid ? warp_sums[wid - 1] : 0;
-  *total = warp_sums[SCAN_BLOCK / 32 - 1];
+  *total = warp_sums[BS / 32 - 1];
   __syncthreads();
   return warp_off + x - v;
+}
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  return block_exclusive_scan_t<SCAN_BLOCK>(v, total);
 }
 
 static __global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
@@ -260,11 +263,11 @@ static __global__ void k_scan_finish(uint32_t* __restrict__ out, uint32_t n, con
 //                    at any moment are a few MB and stay in the L2.
 // hb = g >> bin_shift; hb_region[hb] = bucket_start[hb << bin_shift] is where bin hb starts.
 // ---------------------------------------------------------------------------------------------
-constexpr int PART_BLOCK = 256;
+constexpr int PART_BLOCK = 512;
 template <int C>
 __global__ void __launch_bounds__(PART_BLOCK)
 k_partition(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t tile, uint32_t bin_shift, uint32_t n_bins,
-            const uint32_t* __restrict__ bucket_start, uint32_t* __restrict__ bin_cursor,
+            const uint32_t* __restrict__ region_start, uint32_t region_shift, uint32_t* __restrict__ bin_cursor,
             uint32_t* __restrict__ tmp_g, uint32_t* __restrict__ tmp_v) {
   extern __shared__ uint32_t part_smem[];
   uint32_t* hist = part_smem;                 // [n_bins] counts, then running cursors
@@ -301,13 +304,13 @@ k_partition(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t tile, u
       sum += v[q];
     }
     uint32_t total;
-    uint32_t run = block_exclusive_scan(sum, &total);
+    uint32_t run = block_exclusive_scan_t<PART_BLOCK>(sum, &total);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const uint32_t b = threadIdx.x * 4 + q;
       if (b < n_bins) {
         off[b] = run;
-        gbase[b] = v[q] ? bucket_start[b << bin_shift] + atomicAdd(&bin_cursor[b], v[q]) : 0;
+        gbase[b] = v[q] ? region_start[b << region_shift] + atomicAdd(&bin_cursor[b], v[q]) : 0;
         hist[b] = 0;
       }
       run += v[q];
@@ -359,14 +362,15 @@ template <int C> inline cudaError_t partition_set_smem(size_t bytes) {
 }
 inline cudaError_t launch_partition(uint32_t grid, size_t smem, cudaStream_t st, const uint32_t* scalars,
                                     const Geometry& geo, uint32_t tile, uint32_t bin_shift, uint32_t n_bins,
-                                    const uint32_t* bucket_start, uint32_t* bin_cursor, uint32_t* tmp_g, uint32_t* tmp_v) {
+                                    const uint32_t* region_start, uint32_t region_shift, uint32_t* bin_cursor,
+                                    uint32_t* tmp_g, uint32_t* tmp_v) {
   cudaError_t e = cudaSuccess;
 #define MSM_PART_CASE(CC)                                                                                        \
   case CC:                                                                                                       \
     e = partition_set_smem<CC>(smem);                                                                            \
     if (e == cudaSuccess)                                                                                        \
-      k_partition<CC><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, bucket_start,       \
-                                                      bin_cursor, tmp_g, tmp_v);                                 \
+      k_partition<CC><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, region_start,       \
+                                                      region_shift, bin_cursor, tmp_g, tmp_v);                   \
     break;
   switch (geo.c) {
     MSM_PART_CASE(16) MSM_PART_CASE(17) MSM_PART_CASE(18) MSM_PART_CASE(19) MSM_PART_CASE(20)
@@ -374,12 +378,208 @@ inline cudaError_t launch_partition(uint32_t grid, size_t smem, cudaStream_t st,
     default:
       e = partition_set_smem<0>(smem);
       if (e == cudaSuccess)
-        k_partition<0><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, bucket_start, bin_cursor,
-                                                       tmp_g, tmp_v);
+        k_partition<0><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, region_start, region_shift,
+                                                       bin_cursor, tmp_g, tmp_v);
   }
 #undef MSM_PART_CASE
   return e;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Binned sort (large calls): the same two levels, with every per-digit atomic in SHARED memory.
+// The L2 executes ~80 atomics per clock for the whole chip; a 2^24-point call needs 4 x 10^8 of
+// them in the single-level sort above (histogram + scatter) and that is what its 4.9 ms are.  Here:
+//   k_bin_count   coarse histogram (bins = high bits of the bucket id), per-block in shared memory
+//   k_bin_scan    bin offsets, and the number of fixed-size tiles each bin is cut into
+//   k_partition   (above) groups the digits by bin into tmp_g / tmp_v in coalesced runs
+//   k_bin_hist    one block per tile of one bin: shared-memory histogram of the low bits, then one
+//                 global add per non-empty bucket of the tile
+//   (scan)        bucket_start / cursor as before
+//   k_bin_place   one block per tile: reserves the tile's range of every bucket with one atomic per
+//                 non-empty bucket, then places the entries with shared-memory cursors; the writes
+//                 of a tile land in the few hundred KB of its bin's slice of `entries`
+// Tiles make skewed inputs (and the short top window of a folded table, whose digits all fall into
+// the first bins) a matter of more blocks, not of longer ones.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t BIN_TILE = 16384;
+constexpr int BIN_BLOCK = 256;
+constexpr uint32_t BIN_COUNT_SCALARS = 2048;  // scalars per block in k_bin_count
+
+template <int C>
+__global__ void __launch_bounds__(BIN_BLOCK)
+k_bin_count(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t bin_shift, uint32_t n_bins,
+            uint32_t* __restrict__ bin_count) {
+  extern __shared__ uint32_t bin_smem[];
+  for (uint32_t b = threadIdx.x; b < n_bins; b += BIN_BLOCK) bin_smem[b] = 0;
+  __syncthreads();
+  const uint32_t first = blockIdx.x * BIN_COUNT_SCALARS;
+  for (uint32_t t = threadIdx.x; t < BIN_COUNT_SCALARS; t += BIN_BLOCK) {
+    const uint32_t i = first + t;
+    if (i >= geo.L) break;
+    uint32_t k[8];
+    load_scalar(scalars, i, k);
+    const uint32_t base = (i / geo.chunk_len) * geo.W;
+    auto body = [&](uint32_t w, uint32_t bucket, bool) {
+      const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+      atomicAdd(&bin_smem[g >> bin_shift], 1u);
+    };
+    if (C == 0) for_each_digit(k, geo.c, geo.W, body);
+    else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < n_bins; b += BIN_BLOCK)
+    if (bin_smem[b]) atomicAdd(&bin_count[b], bin_smem[b]);
+}
+inline void launch_bin_count(uint32_t grid, cudaStream_t st, const uint32_t* scalars, const Geometry& geo,
+                             uint32_t bin_shift, uint32_t n_bins, uint32_t* bin_count) {
+  const size_t smem = (size_t)n_bins * 4;
+#define MSM_BINC_CASE(CC) \
+  case CC: k_bin_count<CC><<<grid, BIN_BLOCK, smem, st>>>(scalars, geo, bin_shift, n_bins, bin_count); break;
+  switch (geo.c) {
+    MSM_BINC_CASE(8) MSM_BINC_CASE(9) MSM_BINC_CASE(10) MSM_BINC_CASE(11) MSM_BINC_CASE(12) MSM_BINC_CASE(13)
+    MSM_BINC_CASE(14) MSM_BINC_CASE(15) MSM_BINC_CASE(16) MSM_BINC_CASE(17) MSM_BINC_CASE(18) MSM_BINC_CASE(19)
+    MSM_BINC_CASE(20) MSM_BINC_CASE(21) MSM_BINC_CASE(22) MSM_BINC_CASE(23) MSM_BINC_CASE(24)
+    default: k_bin_count<0><<<grid, BIN_BLOCK, smem, st>>>(scalars, geo, bin_shift, n_bins, bin_count);
+  }
+#undef MSM_BINC_CASE
+}
+
+// single block; n_bins <= 4 * SCAN_BLOCK.  bin_start / tile_start have n_bins + 1 elements.
+static __global__ void k_bin_scan(const uint32_t* __restrict__ bin_count, uint32_t n_bins,
+                                  uint32_t* __restrict__ bin_start, uint32_t* __restrict__ tile_start) {
+  uint32_t c[4], tl[4], sc = 0, stl = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t b = threadIdx.x * 4 + q;
+    c[q] = b < n_bins ? bin_count[b] : 0;
+    tl[q] = (c[q] + BIN_TILE - 1) / BIN_TILE;
+    sc += c[q];
+    stl += tl[q];
+  }
+  uint32_t total_c, total_t;
+  uint32_t off_c = block_exclusive_scan(sc, &total_c);
+  uint32_t off_t = block_exclusive_scan(stl, &total_t);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t b = threadIdx.x * 4 + q;
+    if (b < n_bins) {
+      bin_start[b] = off_c;
+      tile_start[b] = off_t;
+    }
+    off_c += c[q];
+    off_t += tl[q];
+  }
+  if (threadIdx.x == 0) {
+    bin_start[n_bins] = total_c;
+    tile_start[n_bins] = total_t;
+  }
+}
+
+// which bin does tile `tile` belong to, and which entries of tmp_* does it cover
+MSM_D bool bin_tile_range(const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ tile_start,
+                          uint32_t n_bins, uint32_t tile, uint32_t& bin, uint32_t& lo, uint32_t& hi) {
+  if (tile >= __ldg(tile_start + n_bins)) return false;
+  uint32_t a = 0, b = n_bins;  // invariant: tile_start[a] <= tile < tile_start[b]
+  while (b - a > 1) {
+    const uint32_t mid = (a + b) >> 1;
+    if (__ldg(tile_start + mid) <= tile) a = mid;
+    else b = mid;
+  }
+  bin = a;
+  lo = __ldg(bin_start + a) + (tile - __ldg(tile_start + a)) * BIN_TILE;
+  hi = min(lo + BIN_TILE, __ldg(bin_start + a + 1));
+  return true;
+}
+
+static __global__ void __launch_bounds__(BIN_BLOCK)
+k_bin_hist(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ bin_start,
+           const uint32_t* __restrict__ tile_start, uint32_t n_bins, uint32_t bin_shift, uint32_t NB,
+           uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t bin_smem[];
+  const uint32_t bpb = 1u << bin_shift;
+  uint32_t bin, lo, hi;
+  if (!bin_tile_range(bin_start, tile_start, n_bins, blockIdx.x, bin, lo, hi)) return;
+  for (uint32_t b = threadIdx.x; b < bpb; b += BIN_BLOCK) bin_smem[b] = 0;
+  __syncthreads();
+  for (uint32_t p = lo + threadIdx.x; p < hi; p += BIN_BLOCK) atomicAdd(&bin_smem[__ldg(tmp_g + p) & (bpb - 1)], 1u);
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < bpb; b += BIN_BLOCK) {
+    const uint32_t c = bin_smem[b], g = (bin << bin_shift) + b;
+    if (c && g < NB) atomicAdd(&counts[g], c);
+  }
+}
+
+// Placement with the tile sorted in shared memory first, so that the entries of one bucket leave as
+// one run of consecutive 4-byte stores (a 32-byte sector for the typical 8 entries per bucket and
+// tile) instead of 8 scattered ones: 4-byte scattered stores cost the L2 as much as atomics do.
+constexpr int PLACE_BLOCK = 1024;
+static __global__ void __launch_bounds__(PLACE_BLOCK)
+k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp_v,
+            const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ tile_start, uint32_t n_bins,
+            uint32_t bin_shift, uint32_t NB, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+  extern __shared__ uint32_t bin_smem[];
+  const uint32_t bpb = 1u << bin_shift;
+  uint32_t* hist = bin_smem;            // [bpb] counts, later running ranks
+  uint32_t* off = hist + bpb;           // [bpb] first slot of the bucket inside the tile
+  uint32_t* gb = off + bpb;             // [bpb] first global position of this tile's share of the bucket
+  uint32_t* stage_v = gb + bpb;         // [BIN_TILE]
+  uint16_t* stage_b = reinterpret_cast<uint16_t*>(stage_v + BIN_TILE);  // [BIN_TILE] low bucket bits (bpb <= 2^13)
+  __shared__ uint32_t warp_sums[PLACE_BLOCK / 32];
+  uint32_t bin, lo, hi;
+  if (!bin_tile_range(bin_start, tile_start, n_bins, blockIdx.x, bin, lo, hi)) return;
+  for (uint32_t b = threadIdx.x; b < bpb; b += PLACE_BLOCK) hist[b] = 0;
+  __syncthreads();
+  for (uint32_t p = lo + threadIdx.x; p < hi; p += PLACE_BLOCK) atomicAdd(&hist[__ldg(tmp_g + p) & (bpb - 1)], 1u);
+  __syncthreads();
+  // exclusive scan of hist over the block: thread t owns buckets [t*ipt, (t+1)*ipt)
+  const uint32_t ipt = (bpb + PLACE_BLOCK - 1) / PLACE_BLOCK;
+  const uint32_t b0 = threadIdx.x * ipt;
+  uint32_t sum = 0;
+  for (uint32_t q = 0; q < ipt; q++) sum += b0 + q < bpb ? hist[b0 + q] : 0;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t v = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= (uint32_t)o) v += y;
+    }
+    warp_sums[lane] = v;
+  }
+  __syncthreads();
+  uint32_t run = (wid ? warp_sums[wid - 1] : 0) + x - sum;
+  for (uint32_t q = 0; q < ipt; q++) {
+    const uint32_t b = b0 + q;
+    if (b < bpb) {
+      const uint32_t c = hist[b], g = (bin << bin_shift) + b;
+      off[b] = run;
+      run += c;
+      gb[b] = (c && g < NB) ? atomicAdd(&cursor[g], c) : 0;
+      hist[b] = 0;
+    }
+  }
+  __syncthreads();
+  for (uint32_t p = lo + threadIdx.x; p < hi; p += PLACE_BLOCK) {
+    const uint32_t lb = __ldg(tmp_g + p) & (bpb - 1);
+    const uint32_t slot = off[lb] + atomicAdd(&hist[lb], 1u);
+    stage_v[slot] = __ldg(tmp_v + p);
+    stage_b[slot] = (uint16_t)lb;
+  }
+  __syncthreads();
+  for (uint32_t slot = threadIdx.x; slot < hi - lo; slot += PLACE_BLOCK) {
+    const uint32_t lb = stage_b[slot];
+    entries[gb[lb] + (slot - off[lb])] = stage_v[slot];
+  }
+}
+inline size_t bin_place_smem(uint32_t bin_shift) { return ((size_t)3 << bin_shift) * 4 + (size_t)BIN_TILE * 6; }
 
 // ---------------------------------------------------------------------------------------------
 // 128-bit vector loads / stores of plain structs (sizeof multiple of 16, 16-byte aligned).

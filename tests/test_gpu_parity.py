@@ -324,6 +324,37 @@ def test_two_level_scatter_path(engine, oracle, ws, curve, c, chunks, monkeypatc
     assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc, 1), "partition + table")
 
 
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("c,chunks,lines,n_sub", [(13, 1, 1, 1), (16, 1, 1, 3), (9, 16, 2, 1), (20, 1, 1, 1), (11, 4, 1, 1)])
+def test_binned_sort_path(engine, oracle, ws, curve, c, chunks, lines, n_sub, monkeypatch):
+    """The binned sort large calls use (coarse shared-memory histogram, partition, per-tile
+    shared-memory histogram and placement), forced on small adversarial inputs: skewed buckets (many
+    tiles in one bin), identity bases, several tasks and lines, pipelined sub-batches, and a window table."""
+    monkeypatch.setenv("MSM_B200_SORT", "binned")
+    monkeypatch.setenv("MSM_B200_PIPELINE", str(n_sub))
+    n = 40000 // lines if chunks == 1 else 4096
+    n -= n % chunks
+    pts, sc = adversarial_inputs(oracle, curve, n * lines)
+    sc = sc[:n]
+    sc[n // 2: n // 2 + n // 4] = sc[20]  # a quarter of the scalars equal: a few very heavy buckets
+    w = ws[curve]
+    w.set_window_bits(c)
+    try:
+        bases_gpu = engine.upload_multiexp_bases(w, pts)
+        got = engine.multiple_multiexp(w, bases_gpu, sc, chunks, 8, True)
+        t = w.timings()
+        assert t["scatter_passes"] == 0 and t["window_bits"] == c
+    finally:
+        w.set_window_bits(0)
+    want = oracle.multiple_multiexp(curve, pts, sc, chunks)
+    assert_same_points(oracle, curve, got, want, f"binned c={c}")
+    if chunks == 1 and lines == 1:
+        bases_gpu.precompute(14)
+        got = engine.multiple_multiexp(w, bases_gpu, sc, 1, 8, True)
+        assert w.timings()["scatter_passes"] == 0
+        assert_same_points(oracle, curve, got, want, "binned + table")
+
+
 def test_bn254_batched_4096(engine, oracle, ws):
     """Shape of ag-cuda-ec/benches/multiexp.rs:19-22,56 scaled down: 64 MSMs of 2^12 points."""
     curve, chunks, cl = 0, 64, 4096
