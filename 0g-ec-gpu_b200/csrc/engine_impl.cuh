@@ -165,8 +165,16 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   b += Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));              // bucket accumulators (shared by the sub-batches)
   b += Arena::padded((size_t)2 * pl.slices_cap * n_lines * sizeof(Xyzz<F>));  // slice partials
   b += 2 * Arena::padded((size_t)pl.n_tasks * pl.W_sets * pl.PG * sizeof(Xyzz<F>));  // group partials (ping-pong)
-  b += Arena::padded(((size_t)2 * n_lines + (size_t)n_lines * (pl.n_slices / HEAVY_SPAN + 1) +
-                      (size_t)n_lines * pl.slices_cap) * 4);  // cut-bucket and heavy-bucket work lists
+  {
+    // cut-bucket, heavy-bucket and heavy-chunk work lists (FixupLists in enqueue_msm).  Every slice
+    // appends at most one cut bucket; a heavy bucket spans > HEAVY_SPAN slices and spans overlap by
+    // at most one slot, so there are at most slices/HEAVY_SPAN + 1 of them and at most
+    // (slices + heavy)/HEAVY_CHUNK + heavy chunk items.
+    const size_t heavy_cap = pl.slices_cap / HEAVY_SPAN + 1, chunk_cap = 2 * heavy_cap + pl.slices_cap / HEAVY_CHUNK + 2;
+    b += Arena::padded((size_t)3 * n_lines * 4) + Arena::padded((size_t)n_lines * pl.slices_cap * 4) +
+         2 * Arena::padded(n_lines * heavy_cap * 4) + Arena::padded(n_lines * chunk_cap * 4) +
+         Arena::padded(n_lines * chunk_cap * sizeof(Xyzz<F>));
+  }
   pl.scratch_bytes = b;
   return MSM_OK;
 }
@@ -213,13 +221,17 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     uint32_t* tile_sums = dc.arena.take<uint32_t>(n_tiles + 1);
     uint32_t* entries = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
     Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * pl.slices_cap * pl.n_lines);
-    const uint32_t heavy_cap = n_slices / HEAVY_SPAN + 1;
-    // [cut_count | heavy_count | heavy_list | cut_list]
-    uint32_t* cut_count = dc.arena.take<uint32_t>((size_t)2 * pl.n_lines + (size_t)pl.n_lines * (pl.n_slices / HEAVY_SPAN + 1) +
-                                                  (size_t)pl.n_lines * pl.slices_cap);
-    uint32_t* heavy_count = cut_count + pl.n_lines;
-    uint32_t* heavy_list = heavy_count + pl.n_lines;
-    uint32_t* cut_list = heavy_list + (size_t)pl.n_lines * (pl.n_slices / HEAVY_SPAN + 1);
+    FixupLists fl;
+    fl.n_lines = pl.n_lines;
+    fl.cut_cap = pl.slices_cap;
+    fl.heavy_cap = pl.slices_cap / HEAVY_SPAN + 1;
+    fl.chunk_cap = 2 * fl.heavy_cap + pl.slices_cap / HEAVY_CHUNK + 2;
+    fl.counts = dc.arena.take<uint32_t>((size_t)3 * pl.n_lines);
+    fl.cut_list = dc.arena.take<uint32_t>((size_t)pl.n_lines * fl.cut_cap);
+    fl.heavy_list = dc.arena.take<uint32_t>((size_t)pl.n_lines * fl.heavy_cap);
+    fl.heavy_chunk0 = dc.arena.take<uint32_t>((size_t)pl.n_lines * fl.heavy_cap);
+    fl.chunk_list = dc.arena.take<uint32_t>((size_t)pl.n_lines * fl.chunk_cap);
+    Xyzz<F>* chunk_out = dc.arena.take<Xyzz<F>>((size_t)pl.n_lines * fl.chunk_cap);
     Xyzz<F>* acc_sb = bucket_acc;  // every sub-batch continues the same buckets (carry_in)
     const uint32_t carry_in = sb > 0 ? 1u : 0u;
     const uint32_t* sc_sb = d_scalars + (size_t)first * 8;
@@ -307,19 +319,19 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     if (aborted(ctx)) return MSM_ERR_ABORTED;
     // --- accumulate
     dim3 grid((n_slices + tb - 1) / tb, pl.n_lines);
-    // cut_count[n_lines] and heavy_count[n_lines] are adjacent: one memset
-    CU_TRY(ctx, cudaMemsetAsync(cut_count, 0, (size_t)2 * pl.n_lines * 4, st));
+    CU_TRY(ctx, cudaMemsetAsync(fl.counts, 0, (size_t)3 * pl.n_lines * 4, st));
     if (!carry_in) CU_TRY(ctx, cudaMemsetAsync(acc_sb, 0, (size_t)g.NB * pl.n_lines * sizeof(Xyzz<F>), st));  // all infinity
     k_accumulate<F><<<grid, tb, 0, st>>>(bases_sb, line_stride, entries, bucket_start, g.NB, bucket_start + g.NB,
-                                         S, n_slices, acc_sb, partials, carry_in, cut_count, cut_list);
+                                         S, n_slices, acc_sb, partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap);
     // at most one cut bucket per slice
-    k_fixup_cut<F><<<grid, tb, 0, st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials, cut_count, cut_list,
-                                        heavy_count, heavy_list, heavy_cap);
-    const uint32_t hblocks = (heavy_cap + 3) / 4;
+    k_fixup_cut<F><<<grid, tb, 0, st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials, fl);
+    const uint32_t hblocks = (fl.chunk_cap + 3) / 4;
     dim3 hgrid(hblocks < 148 * 8 ? hblocks : 148 * 8, pl.n_lines);
-    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials,
-                                                             heavy_count, heavy_list, heavy_cap);
-    dc.launches += 8;
+    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials, fl,
+                                                             chunk_out);
+    dim3 fgrid2(hblocks < 148 ? hblocks : 148, pl.n_lines);
+    k_fixup_heavy_final<F><<<fgrid2, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, S, acc_sb, fl, chunk_out);
+    dc.launches += 9;
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[3], st));
   if (aborted(ctx)) return MSM_ERR_ABORTED;
@@ -633,7 +645,9 @@ template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint
     for (uint32_t cc = 11; cc <= 24; cc++) {
       const uint32_t W = (bits + 1 + cc - 1) / cc;
       if ((uint64_t)W * sh.n >= (1ull << 31)) continue;
-      const double cost = (double)W * (double)sh.n * 10.0 + (double)(1u << (cc - 1)) * 90.0;
+      // per-bucket figure from measurement (2^21 points, c = 19 -> 20: -0.41 ms accumulate, +0.14 ms reduce)
+      // (below 2^21 points the slices get short and a saved window buys less: measured 2^20, c = 17 beats 19)
+      const double cost = (double)W * (double)sh.n * 10.0 + (double)(1u << (cc - 1)) * (sh.n < (1u << 21) ? 60.0 : 45.0);
       if (cost < best) {
         best = cost;
         c = cc;

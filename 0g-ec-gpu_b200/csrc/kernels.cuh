@@ -667,7 +667,7 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
              const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start,
              uint32_t NB, const uint32_t* __restrict__ E_ptr, uint32_t S, uint32_t n_slices,
              Xyzz<F>* __restrict__ bucket_acc, Xyzz<F>* __restrict__ partials, uint32_t carry_in,
-             uint32_t* __restrict__ cut_count, uint32_t* __restrict__ cut_list) {
+             uint32_t* __restrict__ cut_count, uint32_t* __restrict__ cut_list, uint32_t cut_cap) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t E = __ldg(E_ptr);  // = bucket_start[NB], number of non-zero digits
   if (t >= n_slices || (uint64_t)t * S >= E) return;
@@ -722,7 +722,7 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
   } else {
     store_vec(started_before ? &partials[2 * t] : &partials[2 * t + 1], acc);
     // bucket g starts in this slice and continues in the next one(s): exactly one thread sees that
-    if (!started_before) cut_list[(size_t)line * n_slices + atomicAdd(&cut_count[line], 1u)] = g;
+    if (!started_before) cut_list[(size_t)line * cut_cap + atomicAdd(&cut_count[line], 1u)] = g;
   }
 }
 
@@ -747,22 +747,39 @@ template <class F> MSM_D Xyzz<F> block_sum_xyzz(Xyzz<F> v, Xyzz<F>* sh) {
 // over more than HEAVY_SPAN slices (skewed scalars; the short top window of a folded table) go to
 // a second list that k_fixup_heavy reduces with one warp each.
 constexpr uint32_t HEAVY_SPAN = 16;
+constexpr uint32_t HEAVY_CHUNK = 256;  // partial slots one warp sums in k_fixup_heavy
+// work lists of one line: [cut_count, heavy_count, chunk_count] then the arrays below
+struct FixupLists {
+  uint32_t* counts;        // [3 * n_lines]: cut, heavy, chunk counters of every line
+  uint32_t* cut_list;      // [n_lines * cut_cap]
+  uint32_t* heavy_list;    // [n_lines * heavy_cap] bucket id of every heavy bucket
+  uint32_t* heavy_chunk0;  // [n_lines * heavy_cap] first chunk item of the bucket
+  uint32_t* chunk_list;    // [n_lines * chunk_cap] heavy slot of every chunk item
+  uint32_t cut_cap, heavy_cap, chunk_cap, n_lines;
+};
 template <class F>
 __global__ void __launch_bounds__(128)
 k_fixup_cut(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
-            Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials,
-            const uint32_t* __restrict__ cut_count, const uint32_t* __restrict__ cut_list,
-            uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list, uint32_t heavy_cap) {
+            Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials, FixupLists fl) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t line = blockIdx.y;
-  if (i >= cut_count[line]) return;
+  if (i >= fl.counts[line]) return;
   bucket_acc += (size_t)line * NB;
   partials += (size_t)line * 2 * n_slices;
-  const uint32_t g = cut_list[(size_t)line * n_slices + i];
+  const uint32_t g = fl.cut_list[(size_t)line * fl.cut_cap + i];
   const uint32_t t0 = bucket_start[g] / S, t1 = (bucket_start[g + 1] - 1) / S;
   if (t1 - t0 > HEAVY_SPAN) {
-    const uint32_t slot = atomicAdd(&heavy_count[line], 1u);
-    if (slot < heavy_cap) heavy_list[(size_t)line * heavy_cap + slot] = g;  // cap = n_slices/HEAVY_SPAN + 1 cannot overflow
+    // spread over many slices: one warp per HEAVY_CHUNK partial slots (k_fixup_heavy), so that a
+    // bucket holding a large share of all digits (equal or tiny scalars, a short top window) is
+    // reduced by many warps and not by one
+    const uint32_t nch = (t1 - t0 + 1 + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+    const uint32_t slot = atomicAdd(&fl.counts[fl.n_lines + line], 1u);
+    const uint32_t c0 = atomicAdd(&fl.counts[2 * fl.n_lines + line], nch);
+    if (slot < fl.heavy_cap && c0 + nch <= fl.chunk_cap) {  // the caps cannot be exceeded (see make_plan)
+      fl.heavy_list[(size_t)line * fl.heavy_cap + slot] = g;
+      fl.heavy_chunk0[(size_t)line * fl.heavy_cap + slot] = c0;
+      for (uint32_t q = 0; q < nch; q++) fl.chunk_list[(size_t)line * fl.chunk_cap + c0 + q] = slot;
+    }
     return;
   }
   Xyzz<F> acc = load_vec(&partials[2 * t0 + 1]);
@@ -770,34 +787,69 @@ k_fixup_cut(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, 
   store_vec(&bucket_acc[g], acc);
 }
 
-// One warp per heavy bucket: lane-strided partial sums, then a 5-level tree through shared memory.
+// sum of one value per lane over a warp (5-level tree through shared memory); result in lane 0
+template <class F> MSM_D Xyzz<F> warp_sum_xyzz(Xyzz<F> acc, Xyzz<F>* sh, uint32_t lane) {
+  sh[lane] = acc;
+  __syncwarp();
+  for (uint32_t stride = 16; stride >= 1; stride >>= 1) {
+    if (lane < stride) {
+      acc = xyzz_add<F>(acc, sh[lane + stride]);
+      sh[lane] = acc;
+    }
+    __syncwarp();
+  }
+  return acc;
+}
+
+// One warp per chunk item: lane-strided sums of up to HEAVY_CHUNK partial slots of one heavy
+// bucket, then a warp tree.  A bucket with a single chunk is finished here; otherwise the chunk
+// sums go to chunk_out and k_fixup_heavy_final adds them up.
 template <class F>
 __global__ void __launch_bounds__(128)
 k_fixup_heavy(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S, uint32_t n_slices,
-              Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials,
-              const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list, uint32_t heavy_cap) {
+              Xyzz<F>* __restrict__ bucket_acc, const Xyzz<F>* __restrict__ partials, FixupLists fl,
+              Xyzz<F>* __restrict__ chunk_out) {
   extern __shared__ uint4 smem_raw[];
   Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw) + (threadIdx.x & ~31u);
   const uint32_t line = blockIdx.y, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   bucket_acc += (size_t)line * NB;
   partials += (size_t)line * 2 * n_slices;
-  const uint32_t count = min(heavy_count[line], heavy_cap);
+  chunk_out += (size_t)line * fl.chunk_cap;
+  const uint32_t count = min(fl.counts[2 * fl.n_lines + line], fl.chunk_cap);
   for (uint32_t item = blockIdx.x * warps + (threadIdx.x >> 5); item < count; item += gridDim.x * warps) {
-    const uint32_t g = heavy_list[(size_t)line * heavy_cap + item];
+    const uint32_t slot = fl.chunk_list[(size_t)line * fl.chunk_cap + item];
+    const uint32_t g = fl.heavy_list[(size_t)line * fl.heavy_cap + slot];
+    const uint32_t q = item - fl.heavy_chunk0[(size_t)line * fl.heavy_cap + slot];
     const uint32_t t0 = bucket_start[g] / S, t1 = (bucket_start[g + 1] - 1) / S;
     // element 0 = slot 2*t0+1, element k = slot 2*(t0+k), k = 1 .. t1-t0
+    const uint32_t k_lo = q * HEAVY_CHUNK, k_hi = min(k_lo + HEAVY_CHUNK, t1 - t0 + 1);
     Xyzz<F> acc = xyzz_inf<F>();
-    for (uint32_t k = lane; k <= t1 - t0; k += 32)
+    for (uint32_t k = k_lo + lane; k < k_hi; k += 32)
       acc = xyzz_add<F>(acc, load_vec(k == 0 ? &partials[2 * t0 + 1] : &partials[2 * (t0 + k)]));
-    sh[lane] = acc;
+    acc = warp_sum_xyzz<F>(acc, sh, lane);
+    if (lane == 0) store_vec(t1 - t0 + 1 <= HEAVY_CHUNK ? &bucket_acc[g] : &chunk_out[item], acc);
     __syncwarp();
-    for (uint32_t stride = 16; stride >= 1; stride >>= 1) {
-      if (lane < stride) {
-        acc = xyzz_add<F>(acc, sh[lane + stride]);
-        sh[lane] = acc;
-      }
-      __syncwarp();
-    }
+  }
+}
+template <class F>
+__global__ void __launch_bounds__(128)
+k_fixup_heavy_final(const uint32_t* __restrict__ bucket_start, uint32_t NB, uint32_t S,
+                    Xyzz<F>* __restrict__ bucket_acc, FixupLists fl, const Xyzz<F>* __restrict__ chunk_out) {
+  extern __shared__ uint4 smem_raw[];
+  Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(smem_raw) + (threadIdx.x & ~31u);
+  const uint32_t line = blockIdx.y, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  bucket_acc += (size_t)line * NB;
+  chunk_out += (size_t)line * fl.chunk_cap;
+  const uint32_t count = min(fl.counts[fl.n_lines + line], fl.heavy_cap);
+  for (uint32_t slot = blockIdx.x * warps + (threadIdx.x >> 5); slot < count; slot += gridDim.x * warps) {
+    const uint32_t g = fl.heavy_list[(size_t)line * fl.heavy_cap + slot];
+    const uint32_t span = (bucket_start[g + 1] - 1) / S - bucket_start[g] / S + 1;
+    if (span <= HEAVY_CHUNK) continue;  // finished by k_fixup_heavy
+    const uint32_t nch = (span + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+    const Xyzz<F>* src = chunk_out + fl.heavy_chunk0[(size_t)line * fl.heavy_cap + slot];
+    Xyzz<F> acc = xyzz_inf<F>();
+    for (uint32_t k = lane; k < nch; k += 32) acc = xyzz_add<F>(acc, load_vec(&src[k]));
+    acc = warp_sum_xyzz<F>(acc, sh, lane);
     if (lane == 0) store_vec(&bucket_acc[g], acc);
     __syncwarp();
   }
