@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -66,15 +66,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Rows stamped inside [t0, t1] (the timed region); all rows when no window is given."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         self.thread.join(timeout=2)
-
+        window = "timed region"
+        picked = [r[1:] for r in self.rows if t0 is None or (t0 <= r[0] <= t1 + 0.02)]
+        if len(picked) < 2:
+            # a region shorter than the sampling period (N = 8: 5 steps take 28 ms): use every sample
+            # taken under the same load -- warm-up, timed region and the burst that follows it
+            picked = [r[1:] for r in self.rows]
+            window = "warm-up + timed region + post-region burst of the same step (region shorter than the sampling period)"
+        self.rows = picked
+        self.window = window
         def num(s):
             try:
                 return float(s)
@@ -89,7 +98,7 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
         busy = [c for c, p in zip(sm, pw) if p > 250] or sm
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons, "window": window}
 
 
 def cpu_baseline(curve, log_sample, threads=None):
@@ -290,7 +299,7 @@ def main():
     def step_device():
         rc = lib.msm_multiple_multiexp_device(h, bases, ptr(d_sc), n_local, 1, ptr(d_out))
         assert rc == 0, lib.msm_last_error(h)
-        acc_ms.append(ws.timings()["accumulate_ms"])
+        acc_ms.append(ws.timings())
         combine()
 
     def step_e2e():
@@ -304,15 +313,13 @@ def main():
                 h_out.copy_(d_final)
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
+        t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -321,7 +328,14 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        clocks = sampler.stop() if sampler else None
+        t1 = time.perf_counter()
+        clocks = None
+        if sampler:
+            if t1 - t0 < 0.25:  # keep the same load up until the sampler has seen it
+                while time.perf_counter() - t1 < 0.3:
+                    fn()
+                torch.cuda.synchronize()
+            clocks = sampler.stop(t0, t1)
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -329,13 +343,16 @@ def main():
 
     launches0 = None
     # warm-up happens inside timed(); launches are counted over the timed steps only
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi needs ~0.1 s to deliver its first row: started before the warm-up
     for _ in range(args.warmup):
         step_device()
     launches0 = ws.timings()["kernel_launches"]
     del acc_ms[:]
-    ms_dev, clocks = timed(step_device, args.steps, 0, sample_clocks=True)
-    acc_timed = list(acc_ms)
-    t_last = ws.timings()
+    ms_dev, clocks = timed(step_device, args.steps, 0, sampler=sampler)
+    # the sampler may have kept the load up after the region: only the K timed steps count
+    t_last = acc_ms[args.steps - 1]
+    acc_timed = [t["accumulate_ms"] for t in acc_ms[:args.steps]]
     launches = t_last["kernel_launches"] - launches0
     result_dev = d_final.cpu().numpy().copy() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
@@ -360,14 +377,25 @@ def main():
         roofline["algorithmic_gather_bytes_per_launch"] = n_local * t_last["num_windows"] * 2 * fq
         # sort phase (digit decomposition + histogram + scatter) against HBM
         peaks, peak_src = measured_peaks()
-        sort_bytes = n_local * 32 * (1 + t_last["scatter_passes"]) + n_local * t_last["num_windows"] * 4
+        binned = t_last["scatter_passes"] == 0
+        if binned:
+            # binned sort: scalars read by k_bin_count and twice by k_partition; (bucket, entry) pairs written
+            # once and read by k_bin_hist (bucket ids) and k_bin_place (both); sorted entries written once
+            sort_bytes = n_local * 32 * 3 + n_local * t_last["num_windows"] * (8 + 4 + 8 + 4)
+            kernels = "k_bin_count + k_partition + k_bin_hist + scan + k_bin_place"
+            note = ("32 B/scalar read by 3 passes + per digit: 8 B written and 12 B read of the partitioned "
+                    "(bucket, entry) pairs + 4 B of the sorted entry; all per-digit atomics are in shared memory, "
+                    "the phase is bound by shared-memory atomics and 4-byte store transactions, not by HBM bandwidth")
+        else:
+            sort_bytes = n_local * 32 * (1 + t_last["scatter_passes"]) + n_local * t_last["num_windows"] * 4
+            kernels = "k_digits<count> + scan + k_digits<scatter> x passes"
+            note = ("32 B/scalar read per pass + 4 B written per digit; the phase is bound by L2 atomics and "
+                    "4-byte scattered writes, not by HBM bandwidth")
         sort_gbs = sort_bytes / (t_last["sort_ms"] * 1e-3) / 1e9 if t_last["sort_ms"] > 0 else None
-        roofline_sort = {"bound": "hbm", "kernels": "k_digits<count> + scan + k_digits<scatter> x passes",
+        roofline_sort = {"bound": "hbm", "kernels": kernels,
                          "achieved": sort_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": (sort_gbs / peaks["hbm_gbs"]) if sort_gbs else None, "peak_source": peak_src,
-                         "algorithmic_bytes": sort_bytes, "phase_ms": t_last["sort_ms"],
-                         "note": "32 B/scalar read per pass + 4 B written per digit; the phase is bound by L2 "
-                                 "atomics and 4-byte scattered writes, not by HBM bandwidth (DESIGN.md section 9)"}
+                         "algorithmic_bytes": sort_bytes, "phase_ms": t_last["sort_ms"], "note": note}
         same = bool((to_affine_bytes(lib, h, result_dev, fq) == to_affine_bytes(lib, h, result_e2e, fq)).all())
         name = "BN254 G1" if curve == 0 else "BLS12-381 G1"
         out = {
