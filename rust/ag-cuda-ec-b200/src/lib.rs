@@ -89,6 +89,12 @@ impl Drop for DeviceData {
 pub mod multiexp {
     use super::*;
 
+    /// Engine extension: window table for calls whose tasks have `chunk_len` points each (the
+    /// per-segment commitment and AMT shapes, ag-cuda-ec/benches/{multiexp,amt}.rs).  Results are unchanged.
+    pub fn precompute_chunked_st(bases_gpu: &DeviceData, chunk_len: usize) -> CudaResult<()> {
+        check(GLOBAL.0, unsafe { sys::msm_bases_precompute_chunked(GLOBAL.0, bases_gpu.0, chunk_len) })
+    }
+
     fn upload(ws: &CudaWorkspace, bases: &[Affine]) -> CudaResult<DeviceData> {
         // ag-cuda-ec/src/multiexp.rs:15-16: strip the `infinity` flag, identity -> (0,0)
         let repr: Vec<<Affine as GpuRepr>::Repr> = bases.iter().map(GpuRepr::to_gpu_repr).collect();
@@ -133,6 +139,29 @@ pub mod multiexp {
     ) -> CudaResult<Vec<Curve>> {
         init_local_workspace();
         LOCAL.with(|l| run(l.borrow().as_ref().unwrap(), bases_gpu, exponents, num_chunks, window_size, neg_is_cheap))
+    }
+}
+
+/// ag_cuda_ec::ec_fft (ag-cuda-ec/src/ec_fft.rs:13-99): same signature, the transform runs in msm_ec_fft.
+pub mod ec_fft {
+    use super::*;
+
+    fn run(ws: &CudaWorkspace, input: &mut Vec<Curve>, omegas: &[Scalar]) -> CudaResult<()> {
+        let n = input.len();
+        let log_n = n.ilog2();
+        assert_eq!(n, 1 << log_n);
+        // Vec<Curve> is the {x, y, z} Montgomery record the engine reads and writes in place;
+        // Scalar is arkworks' Fp<MontBackend, 4>: 4 x u64 little-endian, Montgomery form
+        check(ws.0, unsafe {
+            sys::msm_ec_fft(ws.0, input.as_mut_ptr() as *mut c_void, log_n, omegas.as_ptr() as *const c_void, omegas.len() as u32)
+        })
+    }
+    pub fn radix_ec_fft_st(input: &mut Vec<Curve>, omegas: &[Scalar]) -> CudaResult<()> {
+        run(&GLOBAL, input, omegas)
+    }
+    pub fn radix_ec_fft_mt(input: &mut Vec<Curve>, omegas: &[Scalar]) -> CudaResult<()> {
+        init_local_workspace();
+        LOCAL.with(|l| run(l.borrow().as_ref().unwrap(), input, omegas))
     }
 }
 

@@ -49,6 +49,7 @@ extern "C" {
     pub fn msm_bases_upload(ctx: *mut msm_ctx, xy_mont: *const c_void, n_points: usize, out: *mut *mut msm_bases) -> c_int;
     pub fn msm_bases_upload_sharded(ctx: *mut msm_ctx, xy_mont: *const c_void, n_points: usize, out: *mut *mut msm_bases) -> c_int;
     pub fn msm_bases_precompute(ctx: *mut msm_ctx, b: *mut msm_bases, window_bits: u32) -> c_int;
+    pub fn msm_bases_precompute_chunked(ctx: *mut msm_ctx, b: *mut msm_bases, chunk_len: usize) -> c_int;
     pub fn msm_bases_size_bytes(b: *const msm_bases) -> usize;
     pub fn msm_bases_free(b: *mut msm_bases) -> c_int;
     pub fn msm_multiple_multiexp(
@@ -57,4 +58,9 @@ extern "C" {
     ) -> c_int;
     pub fn msm_multiexp(ctx: *mut msm_ctx, bases_xy_mont: *const c_void, scalars: *const c_void, n: usize, out_jacobian: *mut c_void) -> c_int;
     pub fn msm_multiexp_resident(ctx: *mut msm_ctx, bases: *const msm_bases, skip: usize, scalars: *const c_void, n: usize, out_jacobian: *mut c_void) -> c_int;
+    pub fn msm_multiple_multiexp_montgomery(
+        ctx: *mut msm_ctx, bases: *const msm_bases, scalars_mont: *const c_void, l: usize, num_chunks: u32,
+        out_jacobian: *mut c_void,
+    ) -> c_int;
+    pub fn msm_ec_fft(ctx: *mut msm_ctx, jacobian_inout: *mut c_void, log_n: u32, omegas_mont: *const c_void, n_omegas: u32) -> c_int;
 }
