@@ -10,6 +10,7 @@ Contents:
   multiexp.py    mirror of ag_cuda_ec::multiexp (upload_multiexp_bases_*, multiple_multiexp_*)
   kernel.py      mirror of ec_gpu_proxy::multiexp::MultiexpKernel
   ec_fft.py      mirror of ag_cuda_ec::ec_fft (radix_ec_fft_*)
+  fft.py         mirror of ec_gpu_proxy::fft::FftKernel (scalar-field FFT) and ec_gpu_proxy::ec_fft
 """
 from ._lib import (  # noqa: F401
     BLS12_381_G1,
@@ -39,4 +40,5 @@ from .multiexp import (  # noqa: F401
 )
 from .kernel import MultiexpKernel, Worker  # noqa: F401
 from .ec_fft import radix_ec_fft, radix_ec_fft_mt, radix_ec_fft_st  # noqa: F401
+from .fft import EcFftKernel, FftKernel  # noqa: F401
 from .sharding import chunk_size, shard_range  # noqa: F401

@@ -134,6 +134,8 @@ def load_library() -> ctypes.CDLL:
         "msm_sum_points_device": ([vp, vp, sz, vp], i32),
         "msm_ec_fft": ([vp, vp, u32, vp, u32], i32),
         "msm_ec_fft_device": ([vp, vp, u32, vp, u32], i32),
+        "msm_scalar_fft": ([vp, vp, u32, vp], i32),
+        "msm_scalar_fft_device": ([vp, vp, u32, vp], i32),
         "msm_to_affine": ([vp, vp, sz, i32, vp, vp], i32),
         "msm_synth_points_device": ([vp, u64, sz, sz, vp], i32),
         "msm_synth_scalars_device": ([vp, u64, sz, sz, vp], i32),

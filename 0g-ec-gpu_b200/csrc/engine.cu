@@ -7,6 +7,7 @@
 // There is no CPU fallback: without a CUDA device every entry point fails with MSM_ERR_NO_DEVICE.
 #include "engine_common.h"
 #include "kernels.cuh"
+#include "ntt.cuh"
 
 using namespace msm;
 
@@ -62,6 +63,66 @@ const FieldOps* pick_ops(int curve) {
   if (!_lock.ok) return MSM_ERR_BUSY
 
 }  // namespace
+
+// radix_fft (ec-gpu-proxy/src/fft.rs:50-136) over the scalar field of the context's curve.
+template <class PR>
+int scalar_fft_impl(msm_ctx* ctx, void* data, uint32_t log_n, const void* omega_mont, bool device_io) {
+  if (log_n > 27) {
+    set_error(ctx, "scalar fft: at most 2^27 elements");
+    return MSM_ERR_TOO_LARGE;
+  }
+  if (log_n == 0) return MSM_OK;
+  DeviceCtx& dc = ctx->devs[0];
+  CU_TRY(ctx, cudaSetDevice(dc.dev));
+  const size_t n = (size_t)1 << log_n, bytes = n * 32;
+  const uint32_t half = (uint32_t)(n / 2), n_hi = half > 1024 ? half >> 10 : 0;
+  if (!device_io) CU_TRY(ctx, dc.io.ensure(Arena::padded(bytes)));
+  uint32_t* d_x = device_io ? static_cast<uint32_t*>(data) : dc.io.take<uint32_t>(n * 8);
+  CU_TRY(ctx, dc.arena.ensure(Arena::padded(bytes) + Arena::padded((size_t)half * 32) + Arena::padded((size_t)(n_hi + 1) * 32)));
+  uint32_t* d_y = dc.arena.take<uint32_t>(n * 8);
+  uint32_t* d_tw = dc.arena.take<uint32_t>((size_t)half * 8);
+  uint32_t* d_hi = dc.arena.take<uint32_t>((size_t)(n_hi + 1) * 8);
+  Fp<PR> omega;
+  memcpy(omega.v, omega_mont, 32);
+  cudaStream_t st = dc.stream;
+  CU_TRY(ctx, cudaEventRecord(dc.ev[0], st));
+  if (!device_io) CU_TRY(ctx, cudaMemcpyAsync(d_x, data, bytes, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
+  // twiddles: tw[j] = omega^j, j < n/2 -- the first 1024 by the binary method, the rest with one product each
+  const uint32_t low = half < 1024 ? half : 1024;
+  k_ntt_pow_table<PR><<<(low + 127) / 128, 128, 0, st>>>(omega, 0u, low, d_tw);
+  dc.launches += 1;
+  if (n_hi) {
+    k_ntt_pow_table<PR><<<(n_hi + 127) / 128, 128, 0, st>>>(omega, 10u, n_hi, d_hi);
+    k_ntt_expand_table<PR><<<(half - 1024 + 255) / 256, 256, 0, st>>>(d_hi, half, d_tw);
+    dc.launches += 2;
+  }
+  const uint32_t R = log_n < 10 ? log_n : 10;
+  CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_first<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10));
+  CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_pass<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10));
+  k_ntt_first<PR><<<(uint32_t)(n >> R), NTT_BLOCK, (size_t)32 << R, st>>>(d_x, d_y, log_n, R, d_tw);
+  dc.launches += 1;
+  for (uint32_t s0 = R; s0 < log_n;) {
+    if (aborted(ctx)) {  // SingleFftKernel polls maybe_abort once per pass (ec-gpu-proxy/src/fft.rs:86-90)
+      cudaStreamSynchronize(st);
+      return MSM_ERR_ABORTED;
+    }
+    const uint32_t r = log_n - s0 < 5 ? log_n - s0 : 5;
+    k_ntt_pass<PR><<<(uint32_t)(n >> (5 + r)), NTT_BLOCK, (size_t)1024 << r, st>>>(d_y, log_n, s0, r, d_tw);
+    dc.launches += 1;
+    s0 += r;
+  }
+  CU_TRY(ctx, cudaEventRecord(dc.ev[4], st));
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaMemcpyAsync(data, d_y, bytes, device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  msm_timings& t = ctx->tm;
+  memset(&t, 0, sizeof(t));
+  cudaEventElapsedTime(&t.h2d_ms, dc.ev[0], dc.ev[1]);
+  cudaEventElapsedTime(&t.total_ms, dc.ev[1], dc.ev[4]);
+  t.kernel_launches = dc.launches;
+  return MSM_OK;
+}
 
 // =================================================================================================
 extern "C" {
@@ -395,6 +456,21 @@ int msm_ec_fft_device(msm_ctx* ctx, void* d_jacobian_inout, uint32_t log_n, cons
   LOCK_OR_BUSY(ctx);
   if (aborted(ctx)) return MSM_ERR_ABORTED;
   return ctx->ops->ec_fft(ctx, d_jacobian_inout, log_n, omegas_mont, n_omegas, true);
+}
+
+int msm_scalar_fft(msm_ctx* ctx, void* fr_inout, uint32_t log_n, const void* omega_mont) {
+  if (!ctx || !omega_mont || (!fr_inout && log_n)) return MSM_ERR_INVALID;
+  LOCK_OR_BUSY(ctx);
+  if (aborted(ctx)) return MSM_ERR_ABORTED;
+  return ctx->curve == MSM_CURVE_BN254_G1 ? scalar_fft_impl<Bn254Fr>(ctx, fr_inout, log_n, omega_mont, false)
+                                          : scalar_fft_impl<Bls381Fr>(ctx, fr_inout, log_n, omega_mont, false);
+}
+int msm_scalar_fft_device(msm_ctx* ctx, void* d_fr_inout, uint32_t log_n, const void* omega_mont) {
+  if (!ctx || !omega_mont || (!d_fr_inout && log_n)) return MSM_ERR_INVALID;
+  LOCK_OR_BUSY(ctx);
+  if (aborted(ctx)) return MSM_ERR_ABORTED;
+  return ctx->curve == MSM_CURVE_BN254_G1 ? scalar_fft_impl<Bn254Fr>(ctx, d_fr_inout, log_n, omega_mont, true)
+                                          : scalar_fft_impl<Bls381Fr>(ctx, d_fr_inout, log_n, omega_mont, true);
 }
 
 int msm_test_fq_op(msm_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {

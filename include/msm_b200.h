@@ -183,6 +183,16 @@ int msm_ec_fft(msm_ctx* ctx, void* jacobian_inout, uint32_t log_n, const void* o
 int msm_ec_fft_device(msm_ctx* ctx, void* d_jacobian_inout, uint32_t log_n, const void* omegas_mont,
                       uint32_t n_omegas);
 
+/* ---- scalar-field FFT ---------------------------------------------- */
+/* SingleFftKernel::radix_fft (ec-gpu-proxy/src/fft.rs:50-136; KERNEL FIELD_radix_fft,
+ * ag-build/cl/fft.cl:4-66): in-place transform of n = 2^log_n elements of the scalar field Fr of the
+ * context's curve, out[k] = sum_j omega^(j k) in[j], natural order in and out (serial_fft,
+ * ec-gpu-proxy/src/fft_cpu.rs:10-52).  Elements and omega are in arkworks' in-memory Fr layout
+ * (4 x u64 little-endian, Montgomery form, canonical).  Synchronous. */
+int msm_scalar_fft(msm_ctx* ctx, void* fr_inout, uint32_t log_n, const void* omega_mont);
+/* Same with the elements in device memory of device 0 (omega stays a host value). */
+int msm_scalar_fft_device(msm_ctx* ctx, void* d_fr_inout, uint32_t log_n, const void* omega_mont);
+
 /* ---- small device-side helpers used by callers, tests and the bench ----------------------- */
 /* Sum `count` Jacobian points that live in device memory of device 0 into one Jacobian point
  * (device memory): the on-device replacement of the host loop acc.add_assign(&r)

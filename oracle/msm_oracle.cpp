@@ -710,6 +710,41 @@ static void ec_fft_serial(const Curve<N>& cv, const Field<4>& fr, Jac<N>* a, uin
   }
 }
 
+// serial_fft (ec-gpu-proxy/src/fft_cpu.rs:10-52): the same bit-reversal + log_n rounds of butterflies
+// over scalar-field elements (Montgomery form, arkworks' in-memory Fr).
+static void fr_fft_serial(const Field<4>& fr, u64* a, uint32_t log_n, const u64* omega_mont) {
+  const uint32_t n = 1u << log_n;
+  for (uint32_t k = 0; k < n; k++) {
+    uint32_t rk = 0, t = k;
+    for (uint32_t i = 0; i < log_n; i++) { rk = (rk << 1) | (t & 1); t >>= 1; }
+    if (k < rk)
+      for (int q = 0; q < 4; q++) std::swap(a[4 * (size_t)k + q], a[4 * (size_t)rk + q]);
+  }
+  uint32_t m = 1;
+  for (uint32_t round = 0; round < log_n; round++) {
+    u64 w_m[4], base[4];
+    memcpy(w_m, fr.one, sizeof(w_m));
+    memcpy(base, omega_mont, sizeof(base));
+    for (uint32_t e = n / (2 * m); e; e >>= 1) {  // pow_vartime(omega, n / 2m)
+      if (e & 1) fr.mul(w_m, w_m, base);
+      fr.sqr(base, base);
+    }
+    for (uint32_t k = 0; k < n; k += 2 * m) {
+      u64 w[4];
+      memcpy(w, fr.one, sizeof(w));
+      for (uint32_t j = 0; j < m; j++) {
+        u64 *lo = a + 4 * (size_t)(k + j), *hi = a + 4 * (size_t)(k + j + m), t[4], d[4];
+        fr.mul(t, hi, w);
+        fr.sub(d, lo, t);
+        fr.add(lo, lo, t);
+        memcpy(hi, d, sizeof(d));
+        fr.mul(w, w, w_m);
+      }
+    }
+    m *= 2;
+  }
+}
+
 template <int N> static int get_constant(const Curve<N>& c, int which, void* out) {
   switch (which) {
     case 0: memcpy(out, c.fq.p, 8 * N); return 0;
@@ -897,6 +932,13 @@ unsigned oracle_window_for(size_t n) { return window_for(n); }
 int oracle_ec_fft(int curve, void* jac_inout, uint32_t log_n, const void* omega_mont) {
   DISPATCH(curve, ec_fft_serial<4>(g_bn254, g_bn254_fr, (Jac<4>*)jac_inout, log_n, (const u64*)omega_mont),
            ec_fft_serial<6>(g_bls381, g_bls381_fr, (Jac<6>*)jac_inout, log_n, (const u64*)omega_mont));
+  return 0;
+}
+// In-place FFT over Fr elements (Montgomery form); ec-gpu-proxy/src/fft_cpu.rs:10-52.
+int oracle_fr_fft(int curve, void* fr_inout, uint32_t log_n, const void* omega_mont) {
+  init_curves();
+  if (curve != 0 && curve != 1) return -100;
+  fr_fft_serial(curve == 0 ? g_bn254_fr : g_bls381_fr, (u64*)fr_inout, log_n, (const u64*)omega_mont);
   return 0;
 }
 // Fr helpers for tests: op 0 = to Montgomery form, 1 = from Montgomery form, 2 = multiply (Montgomery)

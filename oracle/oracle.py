@@ -50,6 +50,7 @@ def lib():
         _lib.oracle_gen_points.argtypes = [i32, u64, sz, sz, i32, vp]
         _lib.oracle_ec_fft.argtypes = [i32, vp, u32, vp]
         _lib.oracle_fr_op.argtypes = [i32, i32, vp, vp, vp, sz]
+        _lib.oracle_fr_fft.argtypes = [i32, vp, u32, vp]
         _lib.oracle_window_for.argtypes = [sz]
         _lib.oracle_window_for.restype = ctypes.c_uint
     return _lib
@@ -193,6 +194,18 @@ def ec_fft(curve, jac, omega_mont):
     assert 1 << log_n == n
     om = np.ascontiguousarray(omega_mont, dtype=np.uint8)
     rc = lib().oracle_ec_fft(curve, _ptr(out), log_n, _ptr(om))
+    assert rc == 0
+    return out
+
+
+def fr_fft(curve, elems_mont, omega_mont):
+    """serial_fft restated: returns the transformed copy of elems_mont ([n, 32] uint8 Fr Montgomery, n = 2^k)."""
+    out = np.ascontiguousarray(elems_mont, dtype=np.uint8).copy()
+    n = out.size // 32
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    om = np.ascontiguousarray(omega_mont, dtype=np.uint8)
+    rc = lib().oracle_fr_fft(curve, _ptr(out), log_n, _ptr(om))
     assert rc == 0
     return out
 

@@ -63,4 +63,5 @@ extern "C" {
         out_jacobian: *mut c_void,
     ) -> c_int;
     pub fn msm_ec_fft(ctx: *mut msm_ctx, jacobian_inout: *mut c_void, log_n: u32, omegas_mont: *const c_void, n_omegas: u32) -> c_int;
+    pub fn msm_scalar_fft(ctx: *mut msm_ctx, fr_inout: *mut c_void, log_n: u32, omega_mont: *const c_void) -> c_int;
 }

@@ -10,8 +10,9 @@
                        POINT_multiexp kernel.  Needs /root/reference; the fixture travels instead.
 
   ec_fft_vectors.json  from oracle/pyref.py: the DFT of G1 points evaluated by its definition.
+  fr_fft_vectors.json  the DFT over the scalar field evaluated by its definition (Python integers).
 
-Run from the repo root:  python tests/golden/make_golden.py   (--only-ec-fft: just the last file)
+Run from the repo root:  python tests/golden/make_golden.py   (--only-fft: just the FFT files)
 """
 import json
 import os
@@ -179,10 +180,32 @@ def make_ec_fft():
         json.dump(out, f, indent=1)
 
 
+def make_fr_fft():
+    """fr_fft_vectors.json: the DFT over the scalar field by its definition in Python integers."""
+    out = {"generator": "tests/golden/make_golden.py make_fr_fft (Python integers, naive O(n^2) DFT)", "curves": {}}
+    R = 1 << 256
+    for cv, g in ((P.BN254, 5), (P.BLS12_381, 7)):
+        rng = np.random.default_rng(4242 + cv.curve_id)
+        cases = []
+        for log_n in (1, 4, 7):
+            n = 1 << log_n
+            omega = pow(g, (cv.r - 1) // n, cv.r)
+            a = [int.from_bytes(rng.bytes(40), "little") % cv.r for _ in range(n)]
+            a[0], a[-1] = 0, cv.r - 1
+            res = [sum(a[j] * pow(omega, j * k % n, cv.r) for j in range(n)) % cv.r for k in range(n)]
+            cases.append({"log_n": log_n, "omega_mont": hx((omega * R % cv.r).to_bytes(32, "little")),
+                          "input_mont": hx(b"".join((x * R % cv.r).to_bytes(32, "little") for x in a)),
+                          "output_mont": hx(b"".join((x * R % cv.r).to_bytes(32, "little") for x in res))})
+        out["curves"][cv.name] = cases
+    with open(os.path.join(HERE, "fr_fft_vectors.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    if "--only-ec-fft" not in sys.argv:
+    if "--only-ec-fft" not in sys.argv and "--only-fft" not in sys.argv:
         make_pyref()
         make_ref_cl()
     make_ec_fft()
-    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json"):
+    make_fr_fft()
+    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json", "fr_fft_vectors.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")

@@ -226,3 +226,16 @@ def test_ec_fft_oracle_inverse_round_trip(oracle, pyref, curve):
     want = np.stack([oracle.scalar_mul(curve, pts[i], np.frombuffer(n.to_bytes(32, "little"), dtype=np.uint8))
                      for i in range(n)])
     assert_same_points(oracle, curve, back, want, "ifft(fft(x)) == n x")
+
+
+# ---------------------------------------------------------------------------------------------
+# Scalar-field FFT: the oracle's restatement of serial_fft
+# (ec-gpu-proxy/src/fft_cpu.rs:10-52) against the transform's definition in Python integers.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", [0, 1])
+def test_fr_fft_oracle_vs_naive_dft_golden(oracle, curve):
+    for case in _load("fr_fft_vectors.json")["curves"][NAMES[curve]]:
+        a = _b(case["input_mont"], 32)
+        want = _b(case["output_mont"], 32)
+        got = oracle.fr_fft(curve, a, _b(case["omega_mont"], 32)[0])
+        assert (got == want).all(), f"log_n={case['log_n']}"
