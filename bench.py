@@ -398,12 +398,14 @@ def main():
                          "algorithmic_bytes": sort_bytes, "phase_ms": t_last["sort_ms"], "note": note}
         same = bool((to_affine_bytes(lib, h, result_dev, fq) == to_affine_bytes(lib, h, result_e2e, fq)).all())
         name = "BN254 G1" if curve == 0 else "BLS12-381 G1"
+        cfg = {(0, 24): "configs[2]", (0, 20): "configs[1]", (1, 22): "configs[3]"}.get((curve, args.log_n),
+                                                                                        "a size outside configs")
         out = {
             "metric": METRIC[curve], "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "%s MSM 2^%d, contiguous shards of 2^%d points per GPU (BASELINE.json configs[2])"
-                                   % (name, args.log_n, n_local.bit_length() - 1),
+            "config": {"workload": "%s MSM 2^%d, contiguous shards of 2^%d points per GPU (BASELINE.json %s)"
+                                   % (name, args.log_n, n_local.bit_length() - 1, cfg),
                        "log_n": args.log_n, "points_per_gpu": n_local, "window_bits": t_last["window_bits"],
                        "num_windows": t_last["num_windows"], "field_impl": lib.msm_field_impl(h).decode(),
                        "seed": SEED,
