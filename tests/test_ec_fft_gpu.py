@@ -94,3 +94,38 @@ def test_ec_fft_argument_errors(engine, oracle, pyref, ws):
     jac = _lift(oracle, 0, oracle.gen_points(0, 1, 16))
     with pytest.raises(engine.CudaError):  # fewer omegas than rounds
         engine.radix_ec_fft(ws[0], jac, _omegas(pyref, 0, 16)[:3])
+
+
+def test_ec_fft_and_fft_in_concurrent_threads(engine, oracle, pyref):
+    """ag-cuda-ec/benches/ec_fft.rs:62-110 (bench_ec_fft_parallel): radix_ec_fft_mt from several host
+    threads at once, each on its thread-local workspace; here together with scalar-field FFTs."""
+    import threading
+
+    curve, log_n = 0, 6
+    n = 1 << log_n
+    r = pyref.CURVES[curve].r
+    omegas = _omegas(pyref, curve, n)
+    inputs = [_lift(oracle, curve, oracle.gen_points(curve, 900 + t, n)) for t in range(4)]
+    want = [oracle.ec_fft(curve, j, omegas[0]) for j in inputs]
+    errs = []
+
+    def work(t):
+        try:
+            engine.radix_ec_fft_mt(inputs[t], omegas, curve)
+            k = engine.FftKernel.create([0], curve)
+            a = oracle.gen_scalars(curve, 50 + t, 1 << 12)
+            om = np.frombuffer((pow(GEN[curve], (r - 1) >> 12, r) * (1 << 256) % r).to_bytes(32, "little"), dtype=np.uint8).copy()
+            ref = oracle.fr_fft(curve, a, om)
+            k.radix_fft(a, om, 12)
+            assert (a == ref).all()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for t in range(4):
+        assert_same_points(oracle, curve, inputs[t], want[t], f"thread {t}")

@@ -457,3 +457,90 @@ def test_multi_device_split_and_gather(engine, oracle):
         assert lib.msm_bases_precompute(kern.workspace.handle, res, 0) == 0
         assert_same_points(oracle, curve, kern.multiexp_resident(res, sc, 0), want, "resident shards + tables")
         lib.msm_bases_free(res)
+
+
+def test_concurrent_local_workspaces(engine, oracle):
+    """The `_mt` entry points give every host thread its own workspace (construct_workspace!,
+    ag-cuda-workspace-macro/src/lib.rs:58-78; ag-cuda-ec/benches/ec_fft.rs:62-110 drives 32 of them at
+    once): four threads, each with its own context on the same GPU, run different MSMs concurrently."""
+    import threading
+
+    curve = 0
+    jobs = []
+    for t in range(4):
+        n = 3000 + 517 * t
+        jobs.append((oracle.gen_points(curve, 100 + t, n), oracle.gen_scalars(curve, 200 + t, n)))
+    want = [oracle.multiple_multiexp(curve, p, s, 4) for p, s in jobs]
+    got, errs = [None] * 4, []
+
+    def work(t):
+        try:
+            for _ in range(3):
+                bases = engine.upload_multiexp_bases_mt(jobs[t][0], curve)
+                got[t] = engine.multiple_multiexp_mt(bases, jobs[t][1], 4, 8, True)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for t in range(4):
+        assert_same_points(oracle, curve, got[t], want[t], f"thread {t}")
+
+
+def test_full_size_default_path_properties(engine, oracle, ws):
+    """BASELINE.json configs[2] at its full size, 2^24 BN254 points, through the path bench.py times:
+    window table (c = 22), binned sort, host scalars uploaded in 8 pipelined sub-batches.  The oracle
+    would need minutes at this size, so size-independent properties pin the result:
+      * the device-resident call and the pipelined host call agree;
+      * the whole MSM equals the sum of 16 chunk MSMs computed without the table (a different window
+        size, sort and reduction);
+      * a 2^14-point prefix agrees with the oracle bit for bit."""
+    curve, n = 0, 1 << 24
+    lib = engine.load_library()
+    w = ws[curve]
+    fq = FQ[curve]
+    h = w.handle
+    dp, ds, do = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    assert lib.msm_device_alloc(h, n * 2 * fq, ctypes.byref(dp)) == 0
+    assert lib.msm_device_alloc(h, n * 32, ctypes.byref(ds)) == 0
+    assert lib.msm_device_alloc(h, 16 * 3 * fq, ctypes.byref(do)) == 0
+    try:
+        assert lib.msm_synth_points_device(h, SEED, 0, n, dp) == 0
+        assert lib.msm_synth_scalars_device(h, SEED, 0, n, ds) == 0
+        bh = ctypes.c_void_p()
+        assert lib.msm_bases_from_device(h, dp, n, ctypes.byref(bh)) == 0
+        # 16 chunks on the plain resident copy
+        assert lib.msm_multiple_multiexp_device(h, bh, ds, n, 16, do) == 0
+        parts = np.zeros((16, 3 * fq), dtype=np.uint8)
+        assert lib.msm_memcpy_d2h(h, parts.ctypes.data, do, parts.nbytes) == 0
+        acc = parts[0:1].copy()
+        for i in range(1, 16):
+            acc = oracle.ec_op(curve, 0, acc, parts[i:i + 1].copy())
+        # whole MSM through the table, device-resident
+        assert lib.msm_bases_precompute(h, bh, 0) == 0
+        assert lib.msm_multiple_multiexp_device(h, bh, ds, n, 1, do) == 0
+        t = w.timings()
+        assert t["window_bits"] == 22 and t["scatter_passes"] == 0
+        whole = np.zeros((1, 3 * fq), dtype=np.uint8)
+        assert lib.msm_memcpy_d2h(h, whole.ctypes.data, do, whole.nbytes) == 0
+        assert_same_points(oracle, curve, whole, acc, "table + binned sort == sum of 16 plain chunks")
+        # the same from host scalars (pipelined sub-batches)
+        sc = np.zeros((n, 32), dtype=np.uint8)
+        assert lib.msm_memcpy_d2h(h, sc.ctypes.data, ds, sc.nbytes) == 0
+        host = np.zeros((1, 3 * fq), dtype=np.uint8)
+        assert lib.msm_multiple_multiexp(h, bh, sc.ctypes.data, n, 1, 8, 1, host.ctypes.data) == 0
+        assert w.timings()["sub_batches"] == 8
+        assert_same_points(oracle, curve, host, whole, "pipelined host scalars == device-resident")
+        # prefix against the oracle
+        m = 1 << 14
+        pts = np.zeros((m, 2 * fq), dtype=np.uint8)
+        assert lib.msm_memcpy_d2h(h, pts.ctypes.data, dp, pts.nbytes) == 0
+        assert (pts == oracle.gen_points(curve, SEED, m)).all() and (sc[:m] == oracle.gen_scalars(curve, SEED, m)).all()
+        lib.msm_bases_free(bh)
+    finally:
+        for d in (dp, ds, do):
+            lib.msm_device_free(h, d)
