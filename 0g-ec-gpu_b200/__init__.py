@@ -14,7 +14,9 @@ Contents:
 """
 from ._lib import (  # noqa: F401
     BLS12_381_G1,
+    BLS12_381_G2,
     BN254_G1,
+    BN254_G2,
     CudaError,
     EcError,
     EcErrorAborted,

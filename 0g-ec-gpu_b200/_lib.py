@@ -17,12 +17,14 @@ _HEADER = os.path.join(_ROOT, "include", "msm_b200.h")
 
 BN254_G1 = 0
 BLS12_381_G1 = 1
+BN254_G2 = 2       # engine extension: the same API over Fq2 coordinates
+BLS12_381_G2 = 3
 
 MSM_OK, MSM_ERR_INVALID, MSM_ERR_CUDA, MSM_ERR_BUSY, MSM_ERR_ABORTED, MSM_ERR_NO_DEVICE, MSM_ERR_TOO_LARGE = range(7)
 
 
 def fq_bytes(curve: int) -> int:
-    return 32 if curve == BN254_G1 else 48
+    return {BN254_G1: 32, BLS12_381_G1: 48, BN254_G2: 64, BLS12_381_G2: 96}[curve]  # bytes per coordinate
 
 
 class EcError(Exception):

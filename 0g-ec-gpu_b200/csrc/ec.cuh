@@ -23,6 +23,7 @@
 #pragma once
 #include "fp.cuh"
 #include "fp29.cuh"
+#include "fp2.cuh"
 
 namespace msm {
 

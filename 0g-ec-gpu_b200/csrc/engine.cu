@@ -31,7 +31,7 @@ struct CtxLock {
 
 ScalarField scalar_field(int curve) {
   ScalarField f;
-  if (curve == MSM_CURVE_BN254_G1) {
+  if (curve_is_bn254(curve)) {
     const uint32_t r[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
                            0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
     memcpy(f.r, r, sizeof(r));
@@ -52,6 +52,8 @@ const FieldOps* pick_ops(int curve) {
   //   u29    BN254 only: nine 29-bit limbs, carry-free IMAD.WIDE (slower on B200)
   const char* env = getenv("MSM_B200_FIELD");
   const bool want_sat = env && (strcmp(env, "sat32") == 0 || strcmp(env, "sat") == 0);
+  if (curve == MSM_CURVE_BN254_G2) return field_ops_bn254_g2();
+  if (curve == MSM_CURVE_BLS12_381_G2) return field_ops_bls381_g2();
   if (curve == MSM_CURVE_BLS12_381_G1) return want_sat ? field_ops_bls381_sat() : field_ops_bls381_lazy();
   if (env && strcmp(env, "u29") == 0) return field_ops_bn254_u29();
   return want_sat ? field_ops_bn254_sat() : field_ops_bn254_lazy();
@@ -127,7 +129,7 @@ int scalar_fft_impl(msm_ctx* ctx, void* data, uint32_t log_n, const void* omega_
 // =================================================================================================
 extern "C" {
 
-const char* msm_version(void) { return "msm_b200 0.2 (sm_100a; bn254: lazy 29-bit limbs, bls12-381: 32-bit limbs)"; }
+const char* msm_version(void) { return "msm_b200 0.3 (sm_100a; BN254 / BLS12-381 G1 and G2, 32-bit-limb Montgomery fields)"; }
 
 int msm_device_count(void) {
   int n = 0;
@@ -139,7 +141,7 @@ int msm_device_count(void) {
 }
 
 int msm_ctx_create(int curve, const int* device_ids, int n_devices, msm_ctx** out) {
-  if (!out || (curve != MSM_CURVE_BN254_G1 && curve != MSM_CURVE_BLS12_381_G1) || n_devices < 0) {
+  if (!out || curve < MSM_CURVE_BN254_G1 || curve > MSM_CURVE_BLS12_381_G2 || n_devices < 0) {
     set_error(nullptr, "msm_ctx_create: invalid argument");
     return MSM_ERR_INVALID;
   }
@@ -405,7 +407,7 @@ int msm_scalars_from_montgomery_device(msm_ctx* ctx, const void* d_in, size_t n,
   DeviceCtx& dc = ctx->devs[0];
   CU_TRY(ctx, cudaSetDevice(dc.dev));
   const uint32_t grid = (uint32_t)((n + 255) / 256);
-  if (ctx->curve == MSM_CURVE_BN254_G1)
+  if (curve_is_bn254(ctx->curve))
     k_scalars_unmont<Bn254Fr><<<grid, 256, 0, dc.stream>>>(static_cast<const uint32_t*>(d_in), (uint32_t)n, static_cast<uint32_t*>(d_out));
   else
     k_scalars_unmont<Bls381Fr><<<grid, 256, 0, dc.stream>>>(static_cast<const uint32_t*>(d_in), (uint32_t)n, static_cast<uint32_t*>(d_out));
@@ -462,14 +464,14 @@ int msm_scalar_fft(msm_ctx* ctx, void* fr_inout, uint32_t log_n, const void* ome
   if (!ctx || !omega_mont || (!fr_inout && log_n)) return MSM_ERR_INVALID;
   LOCK_OR_BUSY(ctx);
   if (aborted(ctx)) return MSM_ERR_ABORTED;
-  return ctx->curve == MSM_CURVE_BN254_G1 ? scalar_fft_impl<Bn254Fr>(ctx, fr_inout, log_n, omega_mont, false)
+  return curve_is_bn254(ctx->curve) ? scalar_fft_impl<Bn254Fr>(ctx, fr_inout, log_n, omega_mont, false)
                                           : scalar_fft_impl<Bls381Fr>(ctx, fr_inout, log_n, omega_mont, false);
 }
 int msm_scalar_fft_device(msm_ctx* ctx, void* d_fr_inout, uint32_t log_n, const void* omega_mont) {
   if (!ctx || !omega_mont || (!d_fr_inout && log_n)) return MSM_ERR_INVALID;
   LOCK_OR_BUSY(ctx);
   if (aborted(ctx)) return MSM_ERR_ABORTED;
-  return ctx->curve == MSM_CURVE_BN254_G1 ? scalar_fft_impl<Bn254Fr>(ctx, d_fr_inout, log_n, omega_mont, true)
+  return curve_is_bn254(ctx->curve) ? scalar_fft_impl<Bn254Fr>(ctx, d_fr_inout, log_n, omega_mont, true)
                                           : scalar_fft_impl<Bls381Fr>(ctx, d_fr_inout, log_n, omega_mont, true);
 }
 

@@ -102,7 +102,8 @@ inline void set_error(msm_ctx* ctx, const std::string& s) {
   else g_create_error = s;
 }
 inline bool aborted(msm_ctx* ctx) { return ctx->abort_flag && *ctx->abort_flag; }
-inline uint32_t scalar_bits(int curve) { return curve == MSM_CURVE_BN254_G1 ? 254 : 255; }
+inline bool curve_is_bn254(int curve) { return curve == MSM_CURVE_BN254_G1 || curve == MSM_CURVE_BN254_G2; }
+inline uint32_t scalar_bits(int curve) { return curve_is_bn254(curve) ? 254 : 255; }
 
 #define CU_TRY(ctx, call)                                                                   \
   do {                                                                                      \
@@ -139,5 +140,7 @@ const FieldOps* field_ops_bn254_sat();
 const FieldOps* field_ops_bls381_sat();
 const FieldOps* field_ops_bn254_lazy();
 const FieldOps* field_ops_bls381_lazy();
+const FieldOps* field_ops_bn254_g2();
+const FieldOps* field_ops_bls381_g2();
 
 }  // namespace msm

@@ -69,6 +69,11 @@ inline uint32_t choose_table_window(uint32_t chunk_len, uint32_t bits, uint64_t 
   return best_c;
 }
 
+// which curve a field class belongs to, from its word count: 8 / 12 = BN254 / BLS12-381 Fq, 16 / 24 = their Fq2
+template <class F> constexpr bool is_bn254() { return F::API_WORDS == 8 || F::API_WORDS == 16; }
+template <class F> constexpr bool is_ext2() { return F::API_WORDS == 16 || F::API_WORDS == 24; }
+template <class F> using BaseParams = typename std::conditional<is_bn254<F>(), Bn254Fq, Bls381Fq>::type;
+
 struct Plan {
   Geometry geo;
   uint32_t n_lines, S, n_slices, Q, RW, PG, n_tasks;
@@ -677,8 +682,17 @@ template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint
 
 // canonical generator in the API layout (Montgomery), computed with the host build of the field
 template <class F> ApiAffine<F> host_generator_api() {
+  using BP = BaseParams<F>;
+  constexpr int NB = BP::N;
+  constexpr int COMPONENTS = F::API_WORDS / NB;  // 1: G1, 2: G2 (c0 | c1)
   uint32_t gx[F::API_WORDS] = {0}, gy[F::API_WORDS] = {0};
-  if (F::API_WORDS == 8) {  // BN254 G1: (1, 2)
+  if (is_ext2<F>()) {
+    for (int c = 0; c < 2; c++)
+      for (int i = 0; i < NB; i++) {
+        gx[c * NB + i] = is_bn254<F>() ? Bn254G2Gen::W(c, i < 8 ? i : 0) : Bls381G2Gen::W(c, i < 12 ? i : 0);
+        gy[c * NB + i] = is_bn254<F>() ? Bn254G2Gen::W(2 + c, i < 8 ? i : 0) : Bls381G2Gen::W(2 + c, i < 12 ? i : 0);
+      }
+  } else if (is_bn254<F>()) {  // BN254 G1: (1, 2)
     gx[0] = 1;
     gy[0] = 2;
   } else {  // BLS12-381 G1
@@ -686,24 +700,25 @@ template <class F> ApiAffine<F> host_generator_api() {
                             0x9774b905u, 0xc3688c4fu, 0x4fa9ac0fu, 0x2695638cu, 0x3197d794u, 0x17f1d3a7u};
     const uint32_t y[12] = {0x46c5e7e1u, 0x0caa2329u, 0xa2888ae4u, 0xd03cc744u, 0x2c04b3edu, 0x00db18cbu,
                             0xd5d00af6u, 0xfcf5e095u, 0x741d8ae4u, 0xa09e30edu, 0xe3aaa0f1u, 0x08b3f481u};
-    for (int i = 0; i < F::API_WORDS; i++) {
+    for (int i = 0; i < NB && i < 12; i++) {
       gx[i] = x[i];
       gy[i] = y[i];
     }
   }
-  // integer -> API Montgomery form: multiply the "value whose API form is the integer" by R
-  using Sat = FieldSat<typename std::conditional<F::API_WORDS == 8, Bn254Fq, Bls381Fq>::type>;
+  // integer -> API Montgomery form, component by component
   ApiAffine<F> g;
-  typename Sat::Elem ex, ey;
-  for (int i = 0; i < F::API_WORDS; i++) {
-    ex.v[i] = gx[i];
-    ey.v[i] = gy[i];
-  }
-  ex = fp_to_mont<typename std::conditional<F::API_WORDS == 8, Bn254Fq, Bls381Fq>::type>(ex);
-  ey = fp_to_mont<typename std::conditional<F::API_WORDS == 8, Bn254Fq, Bls381Fq>::type>(ey);
-  for (int i = 0; i < F::API_WORDS; i++) {
-    g.x[i] = ex.v[i];
-    g.y[i] = ey.v[i];
+  for (int c = 0; c < COMPONENTS; c++) {
+    Fp<BP> ex, ey;
+    for (int i = 0; i < NB; i++) {
+      ex.v[i] = gx[c * NB + i];
+      ey.v[i] = gy[c * NB + i];
+    }
+    ex = fp_to_mont<BP>(ex);
+    ey = fp_to_mont<BP>(ey);
+    for (int i = 0; i < NB; i++) {
+      g.x[c * NB + i] = ex.v[i];
+      g.y[c * NB + i] = ey.v[i];
+    }
   }
   return g;
 }
@@ -745,9 +760,9 @@ int test_fq_impl(msm_ctx* ctx, int op, const void* a, const void* b, void* out, 
   ApiElem<F>* dout = dc.io.take<ApiElem<F>>(count);
   CU_TRY(ctx, cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, dc.stream));
   if (b) CU_TRY(ctx, cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, dc.stream));
-  using SatP = typename std::conditional<F::API_WORDS == 8, Bn254Fq, Bls381Fq>::type;
-  ApiElem<F> r2;
-  for (int i = 0; i < F::API_WORDS; i++) r2.w[i] = SatP::R2(i);
+  using SatP = BaseParams<F>;
+  ApiElem<F> r2;  // R^2 mod p (Fq2: (R^2, 0))
+  for (int i = 0; i < F::API_WORDS; i++) r2.w[i] = i < SatP::N ? SatP::R2(i < SatP::N ? i : 0) : 0u;
   k_test_fq<F><<<(uint32_t)((count + 127) / 128), 128, 0, dc.stream>>>(op, da, b ? db : nullptr, r2, dout, (uint32_t)count);
   dc.launches += 1;
   CU_TRY(ctx, cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, dc.stream));
@@ -807,7 +822,7 @@ template <class F> int sum_points_impl(msm_ctx* ctx, const void* d_in, size_t co
 // device_io: jac is a device pointer on device 0 (omegas are always a small host array).
 template <class F>
 int ec_fft_impl(msm_ctx* ctx, void* jac, uint32_t log_n, const void* omegas_mont, uint32_t n_omegas, bool device_io) {
-  using PR = typename std::conditional<F::API_WORDS == 8, Bn254Fr, Bls381Fr>::type;
+  using PR = typename std::conditional<is_bn254<F>(), Bn254Fr, Bls381Fr>::type;
   if (log_n > 26 || n_omegas < log_n || n_omegas > 64) {
     set_error(ctx, "ec_fft: need 2^log_n <= 2^26 points and omegas[i] = omega^(2^i) for i < log_n");
     return MSM_ERR_INVALID;

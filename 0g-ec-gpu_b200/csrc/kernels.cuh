@@ -660,9 +660,10 @@ MSM_D uint32_t find_bucket(const uint32_t* __restrict__ bucket_start, uint32_t N
 // Bucket accumulation.  Thread t of line `blockIdx.y` owns sorted entries [t*S, (t+1)*S).
 // ---------------------------------------------------------------------------------------------
 // Resident blocks per SM: 4 for 8-limb fields (106 registers), 3 for 12-limb fields (168 registers);
-// measured: 5 blocks (spills) gains nothing for BN254, forcing 4 on BLS12-381 costs 5 %.
+// measured: 5 blocks (spills) gains nothing for BN254, forcing 4 on BLS12-381 costs 5 %.  The Fq2
+// instantiations (16 / 24 words per element) take the full register file.
 template <class F>
-__global__ void __launch_bounds__(128, (F::N <= 9 ? 4 : 3))
+__global__ void __launch_bounds__(128, (F::N <= 9 ? 4 : F::N <= 12 ? 3 : F::N <= 16 ? 2 : 1))
 k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
              const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start,
              uint32_t NB, const uint32_t* __restrict__ E_ptr, uint32_t S, uint32_t n_slices,

@@ -49,7 +49,11 @@ typedef enum {
   MSM_ERR_TOO_LARGE = 6    /* sizes beyond the u32 index space the reference also assumes */
 } msm_status;
 
-typedef enum { MSM_CURVE_BN254_G1 = 0, MSM_CURVE_BLS12_381_G1 = 1 } msm_curve;
+/* G2: the same engine over Fq2 = Fq[u]/(u^2+1); a coordinate is {c0, c1}, each in
+ * the base field's layout (GpuRepr for the quadratic extension, ag-types/src/impls.rs:36-46): points are
+ * 128 B (BN254) / 192 B (BLS12-381) affine and 192 / 288 B Jacobian.  Every entry point below works for all
+ * four ids; "N" in the layout notes is then 16 / 24. */
+typedef enum { MSM_CURVE_BN254_G1 = 0, MSM_CURVE_BLS12_381_G1 = 1, MSM_CURVE_BN254_G2 = 2, MSM_CURVE_BLS12_381_G2 = 3 } msm_curve;
 
 typedef struct msm_ctx msm_ctx;     /* = CudaWorkspace / MultiexpKernel (one or more devices) */
 typedef struct msm_bases msm_bases; /* = DeviceData holding resident bases */

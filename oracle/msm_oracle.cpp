@@ -192,6 +192,58 @@ template <int N> struct Field {
 };
 
 // ----------------------------------------------------------------------------
+// Quadratic extension Fq2 = Fq[u]/(u^2 + 1) with the interface of Field<N> on arrays c0 | c1 of
+// 2 NB limbs (FIELD2 of ag-build/cl/field2.cl:1-61; GpuRepr of the quadratic extension,
+// ag-types/src/impls.rs:36-46; arkworks' Fp2 with NONRESIDUE = -1 for BN254 and BLS12-381).
+// Schoolbook product (4 base products) on purpose: the engine uses fused double-products.
+// ----------------------------------------------------------------------------
+template <int NB> struct Field2 {
+  static constexpr int N = 2 * NB;
+  Field<NB> f;
+  u64 p[N];    // (p, 0): only reported through oracle_constant
+  u64 one[N];  // (R mod p, 0)
+  u64 r2[N];   // (R^2 mod p, 0)
+  u64 inv;
+
+  void init(const u64* modulus) {
+    f.init(modulus);
+    memset(p, 0, sizeof(p));
+    memset(one, 0, sizeof(one));
+    memset(r2, 0, sizeof(r2));
+    memcpy(p, f.p, sizeof(f.p));
+    memcpy(one, f.one, sizeof(f.one));
+    memcpy(r2, f.r2, sizeof(f.r2));
+    inv = f.inv;
+  }
+  inline void add(u64* r, const u64* a, const u64* b) const { f.add(r, a, b); f.add(r + NB, a + NB, b + NB); }
+  inline void sub(u64* r, const u64* a, const u64* b) const { f.sub(r, a, b); f.sub(r + NB, a + NB, b + NB); }
+  inline void neg(u64* r, const u64* a) const { f.neg(r, a); f.neg(r + NB, a + NB); }
+  inline void dbl(u64* r, const u64* a) const { add(r, a, a); }
+  inline void mul(u64* r, const u64* a, const u64* b) const {
+    u64 t0[NB], t1[NB], t2[NB], t3[NB];
+    f.mul(t0, a, b);
+    f.mul(t1, a + NB, b + NB);
+    f.mul(t2, a, b + NB);
+    f.mul(t3, a + NB, b);
+    f.sub(r, t0, t1);
+    f.add(r + NB, t2, t3);
+  }
+  inline void sqr(u64* r, const u64* a) const { mul(r, a, a); }
+  void to_mont(u64* r, const u64* a) const { f.to_mont(r, a); f.to_mont(r + NB, a + NB); }
+  void from_mont(u64* r, const u64* a) const { f.from_mont(r, a); f.from_mont(r + NB, a + NB); }
+  void inverse(u64* r, const u64* a) const {
+    u64 n0[NB], n1[NB], t[NB];
+    f.sqr(n0, a);
+    f.sqr(n1, a + NB);
+    f.add(n0, n0, n1);
+    f.inverse(t, n0);
+    f.mul(r, a, t);
+    f.mul(n1, a + NB, t);
+    f.neg(r + NB, n1);
+  }
+};
+
+// ----------------------------------------------------------------------------
 // Short-Weierstrass curve y^2 = x^3 + b over Fq, Jacobian coordinates.
 // Formulas: dbl-2009-l, madd-2007-bl, add-2007-bl -- the same EFD formulas as
 // ag-build/cl/ec.cl:17-120 and arkworks 0.4 short_weierstrass::Projective.
@@ -200,8 +252,8 @@ template <int N> struct Field {
 template <int N> struct Jac { u64 x[N], y[N], z[N]; };
 template <int N> struct Aff { u64 x[N], y[N]; };  // (0,0) = identity (impls.rs:51-57)
 
-template <int N> struct Curve {
-  Field<N> fq;
+template <int N, class FQ = Field<N>> struct Curve {
+  FQ fq;
   u64 b_mont[N];
   Aff<N> gen;          // generator, Montgomery form
   u64 r[4];            // scalar-field modulus
@@ -366,6 +418,8 @@ template <int N> struct Curve {
 
 static Curve<4> g_bn254;
 static Curve<6> g_bls381;
+static Curve<8, Field2<4>> g_bn254_g2;   // curve ids 2, 3: G2 over Fq2
+static Curve<12, Field2<6>> g_bls381_g2;
 static Field<4> g_bn254_fr, g_bls381_fr;  // scalar fields (EC-FFT twiddles, Montgomery form like arkworks' Fr)
 
 static void parse_hex(u64* out, int n, const char* hex) {
@@ -420,6 +474,38 @@ static void init_curves() {
     g_bls381.ready = true;
     g_bls381_fr.init(g_bls381.r);
   }
+  {
+    // BN254 G2: y^2 = x^3 + 3/(9+u); generator of ark-bn254 / EIP-197
+    g_bn254_g2.fq.init(g_bn254.fq.p);
+    memcpy(g_bn254_g2.r, g_bn254.r, sizeof(g_bn254.r));
+    g_bn254_g2.scalar_bits = 254;
+    u64 b[8], gx[8], gy[8];
+    parse_hex(b, 4, "2b149d40ceb8aaae81be18991be06ac3b5b4c5e559dbefa33267e6dc24a138e5");
+    parse_hex(b + 4, 4, "009713b03af0fed4cd2cafadeed8fdf4a74fa084e52d1852e4a2bd0685c315d2");
+    parse_hex(gx, 4, "1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed");
+    parse_hex(gx + 4, 4, "198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2");
+    parse_hex(gy, 4, "12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa");
+    parse_hex(gy + 4, 4, "090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b");
+    g_bn254_g2.fq.to_mont(g_bn254_g2.b_mont, b);
+    g_bn254_g2.fq.to_mont(g_bn254_g2.gen.x, gx);
+    g_bn254_g2.fq.to_mont(g_bn254_g2.gen.y, gy);
+    g_bn254_g2.ready = true;
+  }
+  {
+    // BLS12-381 G2: y^2 = x^3 + 4(1+u); generator of ark-bls12-381
+    g_bls381_g2.fq.init(g_bls381.fq.p);
+    memcpy(g_bls381_g2.r, g_bls381.r, sizeof(g_bls381.r));
+    g_bls381_g2.scalar_bits = 255;
+    u64 b[12] = {4, 0, 0, 0, 0, 0, 4, 0, 0, 0, 0, 0}, gx[12], gy[12];
+    parse_hex(gx, 6, "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8");
+    parse_hex(gx + 6, 6, "13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e");
+    parse_hex(gy, 6, "0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801");
+    parse_hex(gy + 6, 6, "0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be");
+    g_bls381_g2.fq.to_mont(g_bls381_g2.b_mont, b);
+    g_bls381_g2.fq.to_mont(g_bls381_g2.gen.x, gx);
+    g_bls381_g2.fq.to_mont(g_bls381_g2.gen.y, gy);
+    g_bls381_g2.ready = true;
+  }
   done.store(1);
 }
 
@@ -447,8 +533,8 @@ static unsigned window_for(size_t n) {
 // One "region" of multiexp_inner (multiexp_cpu.rs:252-318): one window, serial scan.
 // Returns 0, or -1 when an identity base would have been added ("Encountered an
 // identity element in the CRS.", multiexp_cpu.rs:57-61).
-template <int N>
-static int multiexp_window(const Curve<N>& cv, const Aff<N>* bases, const u64* exps, size_t n,
+template <int N, class FQ>
+static int multiexp_window(const Curve<N, FQ>& cv, const Aff<N>* bases, const u64* exps, size_t n,
                            unsigned c, unsigned skip, Jac<N>& out) {
   Jac<N> acc;
   cv.set_inf(acc);
@@ -482,8 +568,8 @@ static int multiexp_window(const Curve<N>& cv, const Aff<N>* bases, const u64* e
   return 0;
 }
 
-template <int N>
-static int multiexp_cpu(const Curve<N>& cv, const Aff<N>* bases, const u64* exps, size_t n,
+template <int N, class FQ>
+static int multiexp_cpu(const Curve<N, FQ>& cv, const Aff<N>* bases, const u64* exps, size_t n,
                         int nthreads, Jac<N>& out) {
   const unsigned c = window_for(n);
   std::vector<unsigned> skips;
@@ -537,8 +623,8 @@ static void gen_scalar(const u64* r, int bits, u64 seed, u64 i, u64* out) {
   }
 }
 
-template <int N>
-static void gen_points(const Curve<N>& cv, u64 seed, size_t start, size_t n, Aff<N>* out,
+template <int N, class FQ>
+static void gen_points(const Curve<N, FQ>& cv, u64 seed, size_t start, size_t n, Aff<N>* out,
                        int nthreads) {
   // P_i = (a + i*b) * G,  a,b 64-bit, b odd
   const u64 a = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ull, 0);
@@ -595,8 +681,8 @@ static void gen_points(const Curve<N>& cv, u64 seed, size_t start, size_t n, Aff
   for (auto& t : th) t.join();
 }
 
-template <int N>
-static int multiple_multiexp(const Curve<N>& cv, const Aff<N>* bases, size_t n_bases,
+template <int N, class FQ>
+static int multiple_multiexp(const Curve<N, FQ>& cv, const Aff<N>* bases, size_t n_bases,
                              const u64* exps, size_t L, uint32_t num_chunks, int nthreads,
                              Jac<N>* out) {
   // ag-cuda-ec/src/multiexp.rs:27-31 and ag-build/cl/multiexp.cl:235-263:
@@ -642,8 +728,8 @@ static int multiple_multiexp(const Curve<N>& cv, const Aff<N>* bases, size_t n_b
   return err.load();
 }
 
-template <int N>
-static void msm_naive(const Curve<N>& cv, const Aff<N>* bases, const u64* exps, size_t n,
+template <int N, class FQ>
+static void msm_naive(const Curve<N, FQ>& cv, const Aff<N>* bases, const u64* exps, size_t n,
                       Jac<N>& out) {
   Jac<N> acc;
   cv.set_inf(acc);
@@ -656,8 +742,8 @@ static void msm_naive(const Curve<N>& cv, const Aff<N>* bases, const u64* exps, 
 }
 
 // k * P for a Jacobian P, k canonical little-endian (double-and-add, MSB first)
-template <int N>
-static void jac_scalar_mul(const Curve<N>& cv, Jac<N>& r, const Jac<N>& p, const u64* k, int words) {
+template <int N, class FQ>
+static void jac_scalar_mul(const Curve<N, FQ>& cv, Jac<N>& r, const Jac<N>& p, const u64* k, int words) {
   Jac<N> acc;
   cv.set_inf(acc);
   for (int i = words * 64 - 1; i >= 0; i--) {
@@ -670,8 +756,8 @@ static void jac_scalar_mul(const Curve<N>& cv, Jac<N>& r, const Jac<N>& p, const
 // serial_ec_fft (ec-gpu-proxy/src/ec_fft_cpu.rs:12-57): bit-reversal, then log_n rounds of
 // butterflies t = w * a[k+j+m]; a[k+j+m] = a[k+j] - t; a[k+j] += t with w running over powers of
 // w_m = omega^(n/2m).  omega is an Fr element in Montgomery form.
-template <int N>
-static void ec_fft_serial(const Curve<N>& cv, const Field<4>& fr, Jac<N>* a, uint32_t log_n, const u64* omega_mont) {
+template <int N, class FQ>
+static void ec_fft_serial(const Curve<N, FQ>& cv, const Field<4>& fr, Jac<N>* a, uint32_t log_n, const u64* omega_mont) {
   const uint32_t n = 1u << log_n;
   for (uint32_t k = 0; k < n; k++) {
     uint32_t rk = 0, t = k;
@@ -745,7 +831,7 @@ static void fr_fft_serial(const Field<4>& fr, u64* a, uint32_t log_n, const u64*
   }
 }
 
-template <int N> static int get_constant(const Curve<N>& c, int which, void* out) {
+template <int N, class FQ> static int get_constant(const Curve<N, FQ>& c, int which, void* out) {
   switch (which) {
     case 0: memcpy(out, c.fq.p, 8 * N); return 0;
     case 1: memcpy(out, c.fq.one, 8 * N); return 0;
@@ -761,31 +847,34 @@ template <int N> static int get_constant(const Curve<N>& c, int which, void* out
 }  // namespace
 
 // =============================================================================
-// C interface (ctypes).  curve: 0 = BN254 G1, 1 = BLS12-381 G1.  All field
+// C interface (ctypes).  curve: 0 = BN254 G1, 1 = BLS12-381 G1, 2 = BN254 G2, 3 = BLS12-381 G2.  All field
 // elements little-endian limbs; points Montgomery {x,y[,z]}; scalars canonical
 // 32-byte little-endian.
 // =============================================================================
-#define DISPATCH(curve, CALL4, CALL6) \
-  do {                                \
-    init_curves();                    \
-    if ((curve) == 0) { CALL4; }      \
-    else if ((curve) == 1) { CALL6; } \
-    else return -100;                 \
+#define DISPATCH(curve, CALL4, CALL6, CALL8, CALL12) \
+  do {                                                \
+    init_curves();                                    \
+    if ((curve) == 0) { CALL4; }                      \
+    else if ((curve) == 1) { CALL6; }                 \
+    else if ((curve) == 2) { CALL8; }                 \
+    else if ((curve) == 3) { CALL12; }                \
+    else return -100;                                 \
   } while (0)
 
 extern "C" {
 
-int oracle_fq_limbs64(int curve) { return curve == 0 ? 4 : curve == 1 ? 6 : -100; }
+int oracle_fq_limbs64(int curve) { return curve == 0 ? 4 : curve == 1 ? 6 : curve == 2 ? 8 : curve == 3 ? 12 : -100; }
 int oracle_scalar_bits(int curve) {
   init_curves();
-  return curve == 0 ? g_bn254.scalar_bits : curve == 1 ? g_bls381.scalar_bits : -100;
+  return (curve == 0 || curve == 2) ? g_bn254.scalar_bits : (curve == 1 || curve == 3) ? g_bls381.scalar_bits : -100;
 }
 
 // which: 0 = p, 1 = R mod p (ONE), 2 = R2, 3 = INV (one u64), 4 = generator {x,y} (Montgomery),
 // 5 = scalar modulus r (4 u64), 6 = curve b (Montgomery)
 int oracle_constant(int curve, int which, void* out) {
   DISPATCH(curve, return get_constant<4>(g_bn254, which, out),
-           return get_constant<6>(g_bls381, which, out));
+           return get_constant<6>(g_bls381, which, out), return get_constant<8>(g_bn254_g2, which, out),
+           return get_constant<12>(g_bls381_g2, which, out));
   return 0;
 }
 
@@ -811,7 +900,7 @@ int oracle_fq_op(int curve, int op, const void* a, const void* b, void* out, siz
       }                                                                                     \
     }                                                                                       \
   }
-  DISPATCH(curve, FQ_BODY(4, g_bn254), FQ_BODY(6, g_bls381));
+  DISPATCH(curve, FQ_BODY(4, g_bn254), FQ_BODY(6, g_bls381), FQ_BODY(8, g_bn254_g2), FQ_BODY(12, g_bls381_g2));
   return 0;
 }
 
@@ -835,7 +924,7 @@ int oracle_ec_op(int curve, int op, const void* a, const void* b, void* out, siz
       }                                                                    \
     }                                                                      \
   }
-  DISPATCH(curve, EC_BODY(4, g_bn254), EC_BODY(6, g_bls381));
+  DISPATCH(curve, EC_BODY(4, g_bn254), EC_BODY(6, g_bls381), EC_BODY(8, g_bn254_g2), EC_BODY(12, g_bls381_g2));
   return 0;
 }
 
@@ -856,7 +945,7 @@ int oracle_to_affine(int curve, const void* jac, size_t count, int mont_out, voi
       }                                                   \
     }                                                     \
   }
-  DISPATCH(curve, AFF_BODY(4, g_bn254), AFF_BODY(6, g_bls381));
+  DISPATCH(curve, AFF_BODY(4, g_bn254), AFF_BODY(6, g_bls381), AFF_BODY(8, g_bn254_g2), AFF_BODY(12, g_bls381_g2));
   return 0;
 }
 
@@ -867,7 +956,7 @@ int oracle_on_curve(int curve, const void* aff_mont, size_t count) {
     for (size_t i = 0; i < count; i++)                              \
       if (!CV.aff_is_identity(pa[i]) && !CV.on_curve(pa[i])) return 1 + (int)(i & 0x3fffffff); \
   }
-  DISPATCH(curve, OC_BODY(4, g_bn254), OC_BODY(6, g_bls381));
+  DISPATCH(curve, OC_BODY(4, g_bn254), OC_BODY(6, g_bls381), OC_BODY(8, g_bn254_g2), OC_BODY(12, g_bls381_g2));
   return 0;
 }
 
@@ -879,14 +968,20 @@ int oracle_multiexp_cpu(int curve, const void* bases, const void* exps, size_t n
            return multiexp_cpu<4>(g_bn254, (const Aff<4>*)bases, (const u64*)exps, n, nthreads,
                                   *(Jac<4>*)out_jac),
            return multiexp_cpu<6>(g_bls381, (const Aff<6>*)bases, (const u64*)exps, n, nthreads,
-                                  *(Jac<6>*)out_jac));
+                                  *(Jac<6>*)out_jac),
+           return multiexp_cpu<8>(g_bn254_g2, (const Aff<8>*)bases, (const u64*)exps, n, nthreads,
+                                  *(Jac<8>*)out_jac),
+           return multiexp_cpu<12>(g_bls381_g2, (const Aff<12>*)bases, (const u64*)exps, n, nthreads,
+                                  *(Jac<12>*)out_jac));
   return 0;
 }
 
 int oracle_msm_naive(int curve, const void* bases, const void* exps, size_t n, void* out_jac) {
   DISPATCH(curve,
            msm_naive<4>(g_bn254, (const Aff<4>*)bases, (const u64*)exps, n, *(Jac<4>*)out_jac),
-           msm_naive<6>(g_bls381, (const Aff<6>*)bases, (const u64*)exps, n, *(Jac<6>*)out_jac));
+           msm_naive<6>(g_bls381, (const Aff<6>*)bases, (const u64*)exps, n, *(Jac<6>*)out_jac),
+           msm_naive<8>(g_bn254_g2, (const Aff<8>*)bases, (const u64*)exps, n, *(Jac<8>*)out_jac),
+           msm_naive<12>(g_bls381_g2, (const Aff<12>*)bases, (const u64*)exps, n, *(Jac<12>*)out_jac));
   return 0;
 }
 
@@ -897,7 +992,11 @@ int oracle_multiple_multiexp(int curve, const void* bases, size_t n_bases, const
            return multiple_multiexp<4>(g_bn254, (const Aff<4>*)bases, n_bases, (const u64*)exps, L,
                                        num_chunks, nthreads, (Jac<4>*)out_jac),
            return multiple_multiexp<6>(g_bls381, (const Aff<6>*)bases, n_bases, (const u64*)exps,
-                                       L, num_chunks, nthreads, (Jac<6>*)out_jac));
+                                       L, num_chunks, nthreads, (Jac<6>*)out_jac),
+           return multiple_multiexp<8>(g_bn254_g2, (const Aff<8>*)bases, n_bases, (const u64*)exps, L,
+                                       num_chunks, nthreads, (Jac<8>*)out_jac),
+           return multiple_multiexp<12>(g_bls381_g2, (const Aff<12>*)bases, n_bases, (const u64*)exps,
+                                       L, num_chunks, nthreads, (Jac<12>*)out_jac));
   return 0;
 }
 
@@ -905,15 +1004,19 @@ int oracle_scalar_mul(int curve, const void* base_aff, const void* scalar32, voi
   DISPATCH(curve,
            g_bn254.scalar_mul(*(Jac<4>*)out_jac, *(const Aff<4>*)base_aff, (const u64*)scalar32, 4),
            g_bls381.scalar_mul(*(Jac<6>*)out_jac, *(const Aff<6>*)base_aff, (const u64*)scalar32,
+                               4),
+           g_bn254_g2.scalar_mul(*(Jac<8>*)out_jac, *(const Aff<8>*)base_aff, (const u64*)scalar32, 4),
+           g_bls381_g2.scalar_mul(*(Jac<12>*)out_jac, *(const Aff<12>*)base_aff, (const u64*)scalar32,
                                4));
   return 0;
 }
 
 int oracle_gen_scalars(int curve, uint64_t seed, size_t start, size_t n, void* out) {
   init_curves();
-  const u64* r = curve == 0 ? g_bn254.r : g_bls381.r;
-  int bits = curve == 0 ? g_bn254.scalar_bits : g_bls381.scalar_bits;
-  if (curve != 0 && curve != 1) return -100;
+  if (curve < 0 || curve > 3) return -100;
+  const bool bn = curve == 0 || curve == 2;  // G2 shares the scalar field of its G1
+  const u64* r = bn ? g_bn254.r : g_bls381.r;
+  int bits = bn ? g_bn254.scalar_bits : g_bls381.scalar_bits;
   u64* o = (u64*)out;
   for (size_t i = 0; i < n; i++) gen_scalar(r, bits, seed, start + i, o + 4 * i);
   return 0;
@@ -921,7 +1024,8 @@ int oracle_gen_scalars(int curve, uint64_t seed, size_t start, size_t n, void* o
 
 int oracle_gen_points(int curve, uint64_t seed, size_t start, size_t n, int nthreads, void* out) {
   DISPATCH(curve, gen_points<4>(g_bn254, seed, start, n, (Aff<4>*)out, nthreads),
-           gen_points<6>(g_bls381, seed, start, n, (Aff<6>*)out, nthreads));
+           gen_points<6>(g_bls381, seed, start, n, (Aff<6>*)out, nthreads), gen_points<8>(g_bn254_g2, seed, start, n, (Aff<8>*)out, nthreads),
+           gen_points<12>(g_bls381_g2, seed, start, n, (Aff<12>*)out, nthreads));
   return 0;
 }
 
@@ -931,21 +1035,22 @@ unsigned oracle_window_for(size_t n) { return window_for(n); }
 // in Fr, Montgomery form (arkworks' in-memory layout).  ec-gpu-proxy/src/ec_fft_cpu.rs:12-57.
 int oracle_ec_fft(int curve, void* jac_inout, uint32_t log_n, const void* omega_mont) {
   DISPATCH(curve, ec_fft_serial<4>(g_bn254, g_bn254_fr, (Jac<4>*)jac_inout, log_n, (const u64*)omega_mont),
-           ec_fft_serial<6>(g_bls381, g_bls381_fr, (Jac<6>*)jac_inout, log_n, (const u64*)omega_mont));
+           ec_fft_serial<6>(g_bls381, g_bls381_fr, (Jac<6>*)jac_inout, log_n, (const u64*)omega_mont), ec_fft_serial<8>(g_bn254_g2, g_bn254_fr, (Jac<8>*)jac_inout, log_n, (const u64*)omega_mont),
+           ec_fft_serial<12>(g_bls381_g2, g_bls381_fr, (Jac<12>*)jac_inout, log_n, (const u64*)omega_mont));
   return 0;
 }
 // In-place FFT over Fr elements (Montgomery form); ec-gpu-proxy/src/fft_cpu.rs:10-52.
 int oracle_fr_fft(int curve, void* fr_inout, uint32_t log_n, const void* omega_mont) {
   init_curves();
-  if (curve != 0 && curve != 1) return -100;
-  fr_fft_serial(curve == 0 ? g_bn254_fr : g_bls381_fr, (u64*)fr_inout, log_n, (const u64*)omega_mont);
+  if (curve < 0 || curve > 3) return -100;
+  fr_fft_serial((curve == 0 || curve == 2) ? g_bn254_fr : g_bls381_fr, (u64*)fr_inout, log_n, (const u64*)omega_mont);
   return 0;
 }
 // Fr helpers for tests: op 0 = to Montgomery form, 1 = from Montgomery form, 2 = multiply (Montgomery)
 int oracle_fr_op(int curve, int op, const void* a, const void* b, void* out, size_t count) {
   init_curves();
-  const Field<4>& fr = curve == 0 ? g_bn254_fr : g_bls381_fr;
-  if (curve != 0 && curve != 1) return -100;
+  if (curve < 0 || curve > 3) return -100;
+  const Field<4>& fr = (curve == 0 || curve == 2) ? g_bn254_fr : g_bls381_fr;
   const u64* pa = (const u64*)a;
   const u64* pb = (const u64*)b;
   u64* po = (u64*)out;

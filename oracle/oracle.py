@@ -17,7 +17,7 @@ _lib = None
 
 BN254_G1 = 0
 BLS12_381_G1 = 1
-FQ_BYTES = {0: 32, 1: 48}
+FQ_BYTES = {0: 32, 1: 48, 2: 64, 3: 96}  # bytes per coordinate (2, 3: G2 over Fq2)
 
 
 def build(force=False):

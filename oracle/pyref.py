@@ -131,7 +131,112 @@ BLS12_381 = CurveParams(
     48,
 )
 
-CURVES = {0: BN254, 1: BLS12_381, "bn254": BN254, "bls12_381": BLS12_381}
+class G2Params(CurveParams):
+    """G2 over Fq2 = Fq[u]/(u^2 + 1): coordinates are pairs (c0, c1) of
+    canonical integers; bytes are c0 | c1, each in the base field's Montgomery layout (GpuRepr of the
+    quadratic extension, ag-types/src/impls.rs:36-46).  `fq_bytes` is the size of one Fq2 coordinate."""
+
+    def __init__(self, name, curve_id, base: CurveParams, b, gx, gy):
+        self.name, self.curve_id = name, curve_id
+        self.p, self.r, self.b, self.g = base.p, base.r, b, (gx, gy)
+        self.base_bytes = base.fq_bytes
+        self.fq_bytes = 2 * base.fq_bytes
+        self.R = base.R
+        self.scalar_bits = base.scalar_bits
+
+    # Fq2 arithmetic on tuples
+    def f2add(self, a, b):
+        return ((a[0] + b[0]) % self.p, (a[1] + b[1]) % self.p)
+
+    def f2sub(self, a, b):
+        return ((a[0] - b[0]) % self.p, (a[1] - b[1]) % self.p)
+
+    def f2mul(self, a, b):
+        return ((a[0] * b[0] - a[1] * b[1]) % self.p, (a[0] * b[1] + a[1] * b[0]) % self.p)
+
+    def f2inv(self, a):
+        t = pow(a[0] * a[0] + a[1] * a[1], -1, self.p)
+        return (a[0] * t % self.p, -a[1] * t % self.p)
+
+    def fq_to_bytes(self, x_mont):
+        return b"".join(int(c).to_bytes(self.base_bytes, "little") for c in x_mont)
+
+    def fq_from_bytes(self, b):
+        n = self.base_bytes
+        return (int.from_bytes(b[:n], "little"), int.from_bytes(b[n : 2 * n], "little"))
+
+    def to_mont(self, x):
+        return tuple(c * self.R % self.p for c in x)
+
+    def from_mont(self, x):
+        ri = pow(self.R, -1, self.p)
+        return tuple(c * ri % self.p for c in x)
+
+    def affine_from_bytes(self, b):
+        n = self.fq_bytes
+        x, y = self.fq_from_bytes(b[:n]), self.fq_from_bytes(b[n : 2 * n])
+        if x == (0, 0) and y == (0, 0):
+            return None
+        return (self.from_mont(x), self.from_mont(y))
+
+    def jacobian_from_bytes(self, b):
+        n = self.fq_bytes
+        X, Y, Z = (self.from_mont(self.fq_from_bytes(b[i * n : (i + 1) * n])) for i in range(3))
+        if Z == (0, 0):
+            return None
+        zi = self.f2inv(Z)
+        zi2 = self.f2mul(zi, zi)
+        return (self.f2mul(X, zi2), self.f2mul(Y, self.f2mul(zi2, zi)))
+
+    def on_curve(self, pt):
+        if pt is None:
+            return True
+        x, y = pt
+        return self.f2sub(self.f2mul(y, y), self.f2add(self.f2mul(self.f2mul(x, x), x), self.b)) == (0, 0)
+
+    def neg(self, pt):
+        return None if pt is None else (pt[0], ((-pt[1][0]) % self.p, (-pt[1][1]) % self.p))
+
+    def add(self, a, b):
+        if a is None:
+            return b
+        if b is None:
+            return a
+        if a[0] == b[0]:
+            if self.f2add(a[1], b[1]) == (0, 0):
+                return None
+            xx = self.f2mul(a[0], a[0])
+            lam = self.f2mul(self.f2add(self.f2add(xx, xx), xx), self.f2inv(self.f2add(a[1], a[1])))
+        else:
+            lam = self.f2mul(self.f2sub(b[1], a[1]), self.f2inv(self.f2sub(b[0], a[0])))
+        x3 = self.f2sub(self.f2sub(self.f2mul(lam, lam), a[0]), b[0])
+        y3 = self.f2sub(self.f2mul(lam, self.f2sub(a[0], x3)), a[1])
+        return (x3, y3)
+
+
+def _f2div(p, a, b):
+    t = pow(b[0] * b[0] + b[1] * b[1], -1, p)
+    bi = (b[0] * t % p, -b[1] * t % p)
+    return ((a[0] * bi[0] - a[1] * bi[1]) % p, (a[0] * bi[1] + a[1] * bi[0]) % p)
+
+
+BN254_G2 = G2Params(
+    "bn254_g2", 2, BN254, _f2div(BN254.p, (3, 0), (9, 1)),  # y^2 = x^3 + 3/(9+u)
+    (10857046999023057135944570762232829481370756359578518086990519993285655852781,
+     11559732032986387107991004021392285783925812861821192530917403151452391805634),
+    (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+     4082367875863433681332203403145435568316851327593401208105741076214120093531),
+)
+BLS12_381_G2 = G2Params(
+    "bls12_381_g2", 3, BLS12_381, (4, 4),  # y^2 = x^3 + 4(1+u)
+    (0x024AA2B2F08F0A91260805272DC51051C6E47AD4FA403B02B4510B647AE3D1770BAC0326A805BBEFD48056C8C121BDB8,
+     0x13E02B6052719F607DACD3A088274F65596BD0D09920B61AB5DA61BBDC7F5049334CF11213945D57E5AC7D055D042B7E),
+    (0x0CE5D527727D6E118CC9CDC6DA2E351AADFD9BAA8CBDD3A76D429A695160D12C923AC9CC3BACA289E193548608B82801,
+     0x0606C4A02EA734CC32ACD2B02BC28B99CB3E287E85A763AF267492AB572E99AB3F370D275CEC1DA1AAA9075FF05F79BE),
+)
+
+CURVES = {0: BN254, 1: BLS12_381, 2: BN254_G2, 3: BLS12_381_G2, "bn254": BN254, "bls12_381": BLS12_381,
+          "bn254_g2": BN254_G2, "bls12_381_g2": BLS12_381_G2}
 
 # Public known answers (canonical affine): EIP-196 / py_ecc alt_bn128 multiples of G.
 BN254_2G = (

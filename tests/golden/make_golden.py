@@ -11,6 +11,7 @@
 
   ec_fft_vectors.json  from oracle/pyref.py: the DFT of G1 points evaluated by its definition.
   fr_fft_vectors.json  the DFT over the scalar field evaluated by its definition (Python integers).
+  g2_vectors.json      G2 over Fq2 from oracle/pyref.py's G2Params (--only-g2 regenerates just this file).
 
 Run from the repo root:  python tests/golden/make_golden.py   (--only-fft: just the FFT files)
 """
@@ -201,11 +202,65 @@ def make_fr_fft():
         json.dump(out, f, indent=1)
 
 
+def make_g2():
+    """g2_vectors.json: G2 over Fq2 from oracle/pyref.py's G2Params (independent big-integer affine
+    arithmetic): Fq2 products, multiples of the generator, the synthetic-input prefix, small MSMs with
+    the edge cases, and one batched shape."""
+    out = {"generator": "tests/golden/make_golden.py make_g2 (oracle/pyref.py G2Params)", "curves": {}}
+    for cv in (P.BN254_G2, P.BLS12_381_G2):
+        rng = np.random.default_rng(3030 + cv.curve_id)
+        rnd = lambda: (int.from_bytes(rng.bytes(cv.base_bytes + 8), "little") % cv.p,  # noqa: E731
+                       int.from_bytes(rng.bytes(cv.base_bytes + 8), "little") % cv.p)
+        c = {}
+        fa, fb = [rnd() for _ in range(8)], [rnd() for _ in range(8)]
+        fa[:2], fb[:2] = [(0, 0), (cv.p - 1, 1)], [(5, 7), (cv.p - 1, cv.p - 1)]
+        c["fq2"] = {"a_mont": [hx(cv.fq_to_bytes(cv.to_mont(x))) for x in fa],
+                    "b_mont": [hx(cv.fq_to_bytes(cv.to_mont(x))) for x in fb],
+                    "ab_mont": [hx(cv.fq_to_bytes(cv.to_mont(cv.f2mul(x, y)))) for x, y in zip(fa, fb)],
+                    "a_inv_mont": [hx(cv.fq_to_bytes(cv.to_mont(cv.f2inv(x)))) for x in fa[1:]]}
+        flat = lambda pt: None if pt is None else [[hex(v) for v in pt[0]], [hex(v) for v in pt[1]]]  # noqa: E731
+        c["kG"] = {str(k): flat(cv.mul(k, cv.g)) for k in (1, 2, 3, 7, cv.r - 1)}
+        n = 12
+        sc = P.gen_scalars(cv, SEED, 0, n)
+        pts = P.gen_points(cv, SEED, 0, n)
+        c["synthetic"] = {"seed": SEED, "scalars": hx(P.scalars_to_bytes(sc)), "points_mont": hx(P.points_to_bytes(cv, pts))}
+        esc, epts = list(sc), list(pts)
+        esc[0], esc[1], esc[2] = 0, 1, cv.r - 1
+        epts[3] = None
+        epts[5], esc[5] = epts[4], esc[4]
+        epts[7], esc[7] = cv.neg(epts[6]), esc[6]
+        esc[8] = (1 << 128) - 1
+        c["msm"] = []
+        for name, s_, p_ in (("random12", sc, pts), ("edge12", esc, epts)):
+            c["msm"].append({"name": name, "scalars": hx(P.scalars_to_bytes(s_)), "points_mont": hx(P.points_to_bytes(cv, p_)),
+                             "result_affine": flat(cv.msm(s_, p_))})
+        L, lines, chunks = 8, 2, 2
+        res = []
+        for line in range(lines):
+            for ch in range(chunks):
+                lo = ch * (L // chunks)
+                res.append(flat(cv.msm(sc[lo:lo + L // chunks], pts[(line * L + lo) % n:][: L // chunks])))
+        bpts = [pts[(i % n)] for i in range(L * lines)]
+        res = []
+        for line in range(lines):
+            for ch in range(chunks):
+                lo = ch * (L // chunks)
+                res.append(flat(cv.msm(sc[lo:lo + L // chunks], bpts[line * L + lo: line * L + lo + L // chunks])))
+        c["multiple_multiexp"] = {"L": L, "lines": lines, "chunks": chunks, "scalars": hx(P.scalars_to_bytes(sc[:L])),
+                                  "points_mont": hx(P.points_to_bytes(cv, bpts)), "results_affine": res}
+        out["curves"][cv.name] = c
+    with open(os.path.join(HERE, "g2_vectors.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    if "--only-ec-fft" not in sys.argv and "--only-fft" not in sys.argv:
+    if "--only-ec-fft" not in sys.argv and "--only-fft" not in sys.argv and "--only-g2" not in sys.argv:
         make_pyref()
         make_ref_cl()
-    make_ec_fft()
-    make_fr_fft()
-    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json", "fr_fft_vectors.json"):
+    if "--only-g2" not in sys.argv:
+        make_ec_fft()
+        make_fr_fft()
+    if "--only-fft" not in sys.argv:
+        make_g2()
+    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json", "fr_fft_vectors.json", "g2_vectors.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")

@@ -1,7 +1,7 @@
 """Shared helpers for the parity tests (test infrastructure)."""
 import numpy as np
 
-FQ = {0: 32, 1: 48}
+FQ = {0: 32, 1: 48, 2: 64, 3: 96}  # bytes per coordinate (2, 3: G2 over Fq2)
 SEED = 0x0BADC0DE
 
 

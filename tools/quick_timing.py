@@ -54,7 +54,7 @@ def main():
                 if it > 0 and (best is None or t["total_ms"] < best["total_ms"]):
                     best = t
             pts = n / (best["total_ms"] * 1e-3)
-            macs = {0: 21760, 1: 48000}[curve]
+            macs = {0: 21760, 1: 48000, 2: 16 * 10 * 400, 3: 16 * 10 * 888}[curve]  # G2: an Fq2 product = 2 (3 N^2 + N) MACs
             print(json.dumps({"log_L": lg, "lines": lines, "chunks": chunks, "log_n": lg, "c": best["window_bits"], "W": best["num_windows"],
                               "total_ms": round(best["total_ms"], 3), "sort_ms": round(best["sort_ms"], 3),
                               "acc_ms": round(best["accumulate_ms"], 3), "red_ms": round(best["reduce_ms"], 3),
