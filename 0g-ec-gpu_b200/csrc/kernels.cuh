@@ -519,10 +519,9 @@ k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp
             uint32_t bin_shift, uint32_t NB, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
   extern __shared__ uint32_t bin_smem[];
   const uint32_t bpb = 1u << bin_shift;
-  uint32_t* hist = bin_smem;            // [bpb] counts, later running ranks
+  uint32_t* hist = bin_smem;            // [bpb] counts, then running ranks, then (global position - slot) of the bucket
   uint32_t* off = hist + bpb;           // [bpb] first slot of the bucket inside the tile
-  uint32_t* gb = off + bpb;             // [bpb] first global position of this tile's share of the bucket
-  uint32_t* stage_v = gb + bpb;         // [BIN_TILE]
+  uint32_t* stage_v = off + bpb;        // [BIN_TILE]
   uint16_t* stage_b = reinterpret_cast<uint16_t*>(stage_v + BIN_TILE);  // [BIN_TILE] low bucket bits (bpb <= 2^13)
   __shared__ uint32_t warp_sums[PLACE_BLOCK / 32];
   uint32_t bin, lo, hi;
@@ -531,7 +530,7 @@ k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp
   __syncthreads();
   for (uint32_t p = lo + threadIdx.x; p < hi; p += PLACE_BLOCK) atomicAdd(&hist[__ldg(tmp_g + p) & (bpb - 1)], 1u);
   __syncthreads();
-  // exclusive scan of hist over the block: thread t owns buckets [t*ipt, (t+1)*ipt)
+  // exclusive scan of hist over the block: thread t owns buckets [t*ipt, (t+1)*ipt), ipt <= 8
   const uint32_t ipt = (bpb + PLACE_BLOCK - 1) / PLACE_BLOCK;
   const uint32_t b0 = threadIdx.x * ipt;
   uint32_t sum = 0;
@@ -555,14 +554,19 @@ k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp
     warp_sums[lane] = v;
   }
   __syncthreads();
+  // the owner keeps (first global position - first slot) of its buckets in registers until the tile is
+  // staged: two shared arrays instead of three let two 1024-thread blocks share an SM
   uint32_t run = (wid ? warp_sums[wid - 1] : 0) + x - sum;
-  for (uint32_t q = 0; q < ipt; q++) {
+  uint32_t delta[8];
+#pragma unroll
+  for (uint32_t q = 0; q < 8; q++) {
     const uint32_t b = b0 + q;
-    if (b < bpb) {
+    delta[q] = 0;
+    if (q < ipt && b < bpb) {
       const uint32_t c = hist[b], g = (bin << bin_shift) + b;
       off[b] = run;
+      delta[q] = ((c && g < NB) ? atomicAdd(&cursor[g], c) : 0u) - run;
       run += c;
-      gb[b] = (c && g < NB) ? atomicAdd(&cursor[g], c) : 0;
       hist[b] = 0;
     }
   }
@@ -574,12 +578,13 @@ k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp
     stage_b[slot] = (uint16_t)lb;
   }
   __syncthreads();
-  for (uint32_t slot = threadIdx.x; slot < hi - lo; slot += PLACE_BLOCK) {
-    const uint32_t lb = stage_b[slot];
-    entries[gb[lb] + (slot - off[lb])] = stage_v[slot];
-  }
+#pragma unroll
+  for (uint32_t q = 0; q < 8; q++)
+    if (q < ipt && b0 + q < bpb) hist[b0 + q] = delta[q];
+  __syncthreads();
+  for (uint32_t slot = threadIdx.x; slot < hi - lo; slot += PLACE_BLOCK) entries[hist[stage_b[slot]] + slot] = stage_v[slot];
 }
-inline size_t bin_place_smem(uint32_t bin_shift) { return ((size_t)3 << bin_shift) * 4 + (size_t)BIN_TILE * 6; }
+inline size_t bin_place_smem(uint32_t bin_shift) { return ((size_t)2 << bin_shift) * 4 + (size_t)BIN_TILE * 6; }
 
 // ---------------------------------------------------------------------------------------------
 // 128-bit vector loads / stores of plain structs (sizeof multiple of 16, 16-byte aligned).
