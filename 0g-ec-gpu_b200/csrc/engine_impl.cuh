@@ -132,7 +132,9 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   {
     const uint64_t total_buckets = (uint64_t)g.NB * n_lines;
     uint32_t Q = 8;
-    while (Q < 256 && total_buckets / Q > 32768) Q <<= 1;  // measured: 2^21 buckets -> Q = 64, 2^18 -> Q = 8
+    // measured: 2^21 buckets -> Q = 64, 2^18 -> Q = 8; beyond 2^21 buckets (many-task shapes) more threads beat
+    // longer serial chains (AMT shape, 10.5 M buckets: Q = 64 5.6 ms, Q = 256 7.4 ms)
+    while (Q < 64 && total_buckets / Q > 32768) Q <<= 1;
     if (const char* env = getenv("MSM_B200_REDUCE_Q")) Q = (uint32_t)atoi(env);
     while (Q > g.B) Q >>= 1;
     pl.Q = Q < 1 ? 1 : Q;

@@ -187,9 +187,10 @@ def ncu_traffic(curve, log_n, n_local):
 def to_affine_bytes(lib, h, jac, fq):
     import numpy as np
 
-    xy = np.zeros(2 * fq, dtype=np.uint8)
-    inf = np.zeros(1, dtype=np.uint8)
-    assert lib.msm_to_affine(h, jac.ctypes.data, 1, 0, xy.ctypes.data, inf.ctypes.data) == 0
+    count = jac.size // (3 * fq)
+    xy = np.zeros(count * 2 * fq, dtype=np.uint8)
+    inf = np.zeros(count, dtype=np.uint8)
+    assert lib.msm_to_affine(h, jac.ctypes.data, count, 0, xy.ctypes.data, inf.ctypes.data) == 0
     return np.concatenate([xy, inf])
 
 
@@ -219,6 +220,10 @@ def main():
     ap.add_argument("--cpu-log-sample", type=int, default=23, help="cpu_baseline sample size (log2)")
     ap.add_argument("--ref-log-sample", type=int, default=21, help="--impl reference sample per step (log2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="msm", choices=["msm", "batched"],
+                    help="msm: one MSM of 2^log_n points (the headline, BASELINE.json configs[1-3]); batched: 1024 "
+                         "independent BN254 MSMs of 2^12 points (configs[4], ag-cuda-ec/benches/multiexp.rs:19-22,56), "
+                         "the tasks split over the ranks, no reduction")
     ap.add_argument("--no-table", action="store_true",
                     help="skip msm_bases_precompute (window table next to the resident bases)")
     args = ap.parse_args()
@@ -258,14 +263,20 @@ def main():
     stream = torch.cuda.current_stream()
     assert lib.msm_set_stream(h, ctypes.c_void_p(stream.cuda_stream)) == 0
 
+    batched = args.workload == "batched"
+    if batched:
+        args.log_n, chunk_len = 22, 4096
+        assert curve == 0 and (1024 % world) == 0, "batched workload: BN254, 1024 tasks split evenly over the ranks"
     n_total = 1 << args.log_n
     start, end = m.shard_range(n_total, world, rank)
     n_local = end - start
+    chunks_local = n_local // chunk_len if batched else 1  # tasks of this rank
+    macs_per_point = 32 * 10 * 136 if batched else MACS_PER_POINT[curve]  # canonical c = 8 for 4096-point MSMs
     d_pts = torch.empty(n_local * 2 * fq, dtype=torch.uint8, device=dev)
     d_sc = torch.empty(n_local * 32, dtype=torch.uint8, device=dev)
-    d_out = torch.zeros(3 * fq, dtype=torch.uint8, device=dev)
-    d_gather = torch.zeros(world * 3 * fq, dtype=torch.uint8, device=dev)
-    d_final = torch.zeros(3 * fq, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(chunks_local * 3 * fq, dtype=torch.uint8, device=dev)
+    d_gather = torch.zeros(world * chunks_local * 3 * fq, dtype=torch.uint8, device=dev)
+    d_final = torch.zeros((world if batched else 1) * chunks_local * 3 * fq, dtype=torch.uint8, device=dev)
     ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     assert lib.msm_synth_points_device(h, SEED, start, n_local, ptr(d_pts)) == 0
     assert lib.msm_synth_scalars_device(h, SEED, start, n_local, ptr(d_sc)) == 0
@@ -275,7 +286,7 @@ def main():
     assert rc == 0, lib.msm_last_error(h)
     if not args.no_table:
         # part of making the bases resident (untimed, like upload_multiexp_bases in the reference API)
-        rc = lib.msm_bases_precompute(h, bases, 0)
+        rc = lib.msm_bases_precompute_chunked(h, bases, chunk_len) if batched else lib.msm_bases_precompute(h, bases, 0)
         assert rc == 0, lib.msm_last_error(h)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
@@ -283,13 +294,16 @@ def main():
     torch.cuda.empty_cache()
     h_sc = torch.empty(n_local * 32, dtype=torch.uint8, pin_memory=True)
     h_sc.copy_(d_sc)
-    h_out = torch.zeros(3 * fq, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.zeros(d_final.numel(), dtype=torch.uint8, pin_memory=True)
+    h_part = torch.zeros(chunks_local * 3 * fq, dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
 
     def combine():
         if world > 1:
             dist.all_gather_into_tensor(d_gather, d_out)
-            if rank == 0:
+            if batched:
+                d_final.copy_(d_gather)  # rank-major = task order: nothing to add up
+            elif rank == 0:
                 assert lib.msm_sum_points_device(h, ptr(d_gather), world, ptr(d_final)) == 0
         else:
             d_final.copy_(d_out)
@@ -297,17 +311,18 @@ def main():
     acc_ms = []
 
     def step_device():
-        rc = lib.msm_multiple_multiexp_device(h, bases, ptr(d_sc), n_local, 1, ptr(d_out))
+        rc = lib.msm_multiple_multiexp_device(h, bases, ptr(d_sc), n_local, chunks_local, ptr(d_out))
         assert rc == 0, lib.msm_last_error(h)
         acc_ms.append(ws.timings())
         combine()
 
     def step_e2e():
-        rc = lib.msm_multiple_multiexp(h, bases, ctypes.c_void_p(h_sc.data_ptr()), n_local, 1, 8, 1,
-                                       ctypes.c_void_p(h_out.data_ptr()))
+        dst = h_part if world > 1 else h_out
+        rc = lib.msm_multiple_multiexp(h, bases, ctypes.c_void_p(h_sc.data_ptr()), n_local, chunks_local, 8, 1,
+                                       ctypes.c_void_p(dst.data_ptr()))
         assert rc == 0, lib.msm_last_error(h)
         if world > 1:
-            d_out.copy_(h_out, non_blocking=True)
+            d_out.copy_(h_part, non_blocking=True)
             combine()
             if rank == 0:
                 h_out.copy_(d_final)
@@ -363,14 +378,14 @@ def main():
         e2e = n_total * args.steps / (ms_e2e * 1e-3)
         # dominant kernel: bucket accumulation of this rank's shard
         acc_avg_ms = sum(acc_timed) / len(acc_timed)
-        macs = n_local * MACS_PER_POINT[curve]
+        macs = n_local * macs_per_point
         achieved = macs / (acc_avg_ms * 1e-3)
         roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved / 1e12,
                     "peak": IMAD_PEAK_NOMINAL / 1e12, "unit": "TMAC/s", "frac": achieved / IMAD_PEAK_NOMINAL,
                     "traffic": None, "avg_kernel_ms": acc_avg_ms, "algorithmic_macs_per_launch": macs,
                     "peak_source": "148 SMs x 64 int32-multiply lanes/clk x 1.965 GHz; tools/imad_peak.cu measured "
                                    "1.852e13 MAC/s (99.5 % of it) on this pool; MEASURED_PEAKS.json has no integer figure",
-                    "whole_step_frac": value / world * MACS_PER_POINT[curve] / IMAD_PEAK_NOMINAL}
+                    "whole_step_frac": value / world * macs_per_point / IMAD_PEAK_NOMINAL}
         traffic, traffic_src = ncu_traffic(curve, args.log_n, n_local)
         roofline["traffic"] = traffic
         roofline["traffic_source"] = traffic_src
@@ -401,10 +416,14 @@ def main():
         cfg = {(0, 24): "configs[2]", (0, 20): "configs[1]", (1, 22): "configs[3]"}.get((curve, args.log_n),
                                                                                         "a size outside configs")
         out = {
-            "metric": METRIC[curve], "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "metric": ("BN254 G1 batched MSM points/sec" if batched else METRIC[curve]), "value": value, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "%s MSM 2^%d, contiguous shards of 2^%d points per GPU (BASELINE.json %s)"
+            "config": {"workload": ("1024 x BN254 G1 MSMs of 2^12 points, %d tasks per GPU, chunked window table "
+                                    "(BASELINE.json configs[4]; roofline at the canonical c = 8 count, 43 520 MAC/point)"
+                                    % chunks_local) if batched else
+                                   "%s MSM 2^%d, contiguous shards of 2^%d points per GPU (BASELINE.json %s)"
                                    % (name, args.log_n, n_local.bit_length() - 1, cfg),
                        "log_n": args.log_n, "points_per_gpu": n_local, "window_bits": t_last["window_bits"],
                        "num_windows": t_last["num_windows"], "field_impl": lib.msm_field_impl(h).decode(),
@@ -414,7 +433,7 @@ def main():
                        "l2": "per-step inputs (bases %d MiB + scalars %d MiB + sorted digits) exceed the 126 MB L2"
                              % (n_local * 2 * fq >> 20, n_local * 32 >> 20)},
             "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": n_total * 32, "d2h_bytes_per_step": world * 3 * fq,
+                    "h2d_bytes_per_step": n_total * 32, "d2h_bytes_per_step": world * chunks_local * 3 * fq,
                     "call": "msm_multiple_multiexp: host scalars (pinned) in, host point out; bases resident as in "
                             "ag_cuda_ec::multiple_multiexp"},
             "gpu_launches": int(launches + (args.steps if world > 1 else 0)),
