@@ -835,10 +835,17 @@ int ec_fft_impl(msm_ctx* ctx, void* jac, uint32_t log_n, const void* omegas_mont
   const uint32_t n = 1u << log_n;
   const size_t jb = (size_t)n * sizeof(ApiJacobian<F>);
   CU_TRY(ctx, dc.io.ensure((device_io ? 0 : Arena::padded(jb)) + Arena::padded((size_t)n_omegas * 32) +
-                           Arena::padded((size_t)(n / 2) * 32)));
+                           Arena::padded((size_t)(n / 2) * 32) + Arena::padded(n / 2)));
   ApiJacobian<F>* d_jac = device_io ? static_cast<ApiJacobian<F>*>(jac) : dc.io.take<ApiJacobian<F>>(n);
   uint32_t* d_omegas = dc.io.take<uint32_t>((size_t)n_omegas * 8);
   uint32_t* d_tw = dc.io.take<uint32_t>((size_t)(n / 2) * 8);
+  // G1: twiddles are stored split by the GLV endomorphism (ecfft.cuh); MSM_B200_ECFFT_GLV=0 keeps them whole
+  const char* glv_env = getenv("MSM_B200_ECFFT_GLV");
+  const bool use_glv = !is_ext2<F>() && !(glv_env && atoi(glv_env) == 0);
+  uint8_t* d_tw_sign = use_glv ? dc.io.take<uint8_t>(n / 2) : nullptr;
+  const GlvParams gp = glv_params(is_bn254<F>());
+  ApiElem<F> beta_api;
+  for (int i = 0; i < F::API_WORDS; i++) beta_api.w[i] = i < 12 ? gp.beta[i < 12 ? i : 0] : 0u;
   CU_TRY(ctx, dc.arena.ensure(Arena::padded((size_t)n * sizeof(Xyzz<F>))));
   Xyzz<F>* x = dc.arena.take<Xyzz<F>>(n);
   cudaStream_t st = dc.stream;
@@ -846,7 +853,7 @@ int ec_fft_impl(msm_ctx* ctx, void* jac, uint32_t log_n, const void* omegas_mont
   if (!device_io) CU_TRY(ctx, cudaMemcpyAsync(d_jac, jac, jb, cudaMemcpyHostToDevice, st));
   CU_TRY(ctx, cudaMemcpyAsync(d_omegas, omegas_mont, (size_t)n_omegas * 32, cudaMemcpyHostToDevice, st));
   CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
-  k_fft_twiddles<PR><<<(n / 2 + 127) / 128, 128, 0, st>>>(d_omegas, n / 2, d_tw);
+  k_fft_twiddles<PR><<<(n / 2 + 127) / 128, 128, 0, st>>>(d_omegas, n / 2, d_tw, gp, d_tw_sign);
   k_fft_load<F><<<(n + 127) / 128, 128, 0, st>>>(d_jac, log_n, x);
   dc.launches += 2;
   for (uint32_t s = 0; s < log_n; s++) {
@@ -855,7 +862,7 @@ int ec_fft_impl(msm_ctx* ctx, void* jac, uint32_t log_n, const void* omegas_mont
       return MSM_ERR_ABORTED;
     }
     const uint32_t m = 1u << s;
-    k_fft_round<F><<<(n / 2 + 63) / 64, 64, 0, st>>>(x, n, m, n / (2 * m), d_tw);
+    k_fft_round<F><<<(n / 2 + 63) / 64, 64, 0, st>>>(x, n, m, n / (2 * m), d_tw, d_tw_sign, beta_api);
     dc.launches += 1;
   }
   k_fft_store<F><<<(n + 127) / 128, 128, 0, st>>>(x, n, d_jac);
