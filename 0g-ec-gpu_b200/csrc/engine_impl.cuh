@@ -261,7 +261,9 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
       CU_TRY(ctx, cudaMemsetAsync(bin_count, 0, (size_t)((char*)bin_start - (char*)bin_count), st));
       launch_bin_count((sg.L + BIN_COUNT_SCALARS - 1) / BIN_COUNT_SCALARS, st, sc_sb, sg, bin_shift, n_bins, bin_count);
       k_bin_scan<<<1, SCAN_BLOCK, 0, st>>>(bin_count, n_bins, bin_start, tile_start);
-      uint32_t tile = 12288 / g.W;
+      uint32_t part_entries = 12288;  // digits staged per k_partition block (8 B each in shared memory)
+      if (const char* env = getenv("MSM_B200_PART_ENTRIES")) part_entries = (uint32_t)atoi(env);
+      uint32_t tile = part_entries / g.W;
       tile = tile > 1024 ? 1024 : (tile < 64 ? 64 : tile);
       const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * g.W) * 4;
       CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, sc_sb, sg, tile, bin_shift, n_bins, bin_start, 0u,

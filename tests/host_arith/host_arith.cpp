@@ -94,6 +94,8 @@ template <class F> static int madd_chain(const uint32_t* pts, size_t m, size_t s
   if (curve == 1 && impl == 0) return CALL(FieldSat<Bls381Fq>);             \
   if (curve == 0 && impl == 2) { using L0 = FieldSatLazy<Bn254Fq>; return CALL(L0); }   \
   if (curve == 1 && impl == 2) { using L1 = FieldSatLazy<Bls381Fq>; return CALL(L1); }  \
+  if (curve == 2 && impl == 2) { using E0 = FieldExt2Lazy<Bn254Fq>; return CALL(E0); }   \
+  if (curve == 3 && impl == 2) { using E1 = FieldExt2Lazy<Bls381Fq>; return CALL(E1); }  \
   return -100;
 
 extern "C" int host_fq_op(int curve, int impl, int op, const void* a, const void* b, const void* r2, void* o, size_t n) {

@@ -5,7 +5,8 @@ same formulas run here against the oracle, for both field implementations:
   impl 0  FieldSat  saturated 32-bit limbs (BN254, BLS12-381)
   impl 1  FieldU29  lazy 29-bit limbs (BN254) -- built with MSM_CHECK_BOUNDS, which aborts the
           process on any 64-bit column overflow or negative limb in the lazy-reduction scheme.
-  impl 2  FieldSatLazy  saturated 32-bit limbs with values in [0, 2p) (the engine's default)
+  impl 2  FieldSatLazy  saturated 32-bit limbs with values in [0, 2p) (the engine's default), and for the
+          G2 curve ids FieldExt2Lazy, the quadratic extension over it (csrc/fp2.cuh)
 """
 import ctypes
 import os
@@ -17,7 +18,8 @@ import pytest
 from util import FQ, assert_same_points
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-IMPLS = [(0, 0), (0, 1), (1, 0), (0, 2), (1, 2)]  # (curve, impl); impl 2 = FieldSatLazy, values in [0, 2p)
+# (curve, impl); impl 2 = FieldSatLazy, values in [0, 2p); curves 2, 3 = G2: FieldExt2Lazy (Fq2 over it, csrc/fp2.cuh)
+IMPLS = [(0, 0), (0, 1), (1, 0), (0, 2), (1, 2), (2, 2), (3, 2)]
 
 
 @pytest.fixture(scope="module")
@@ -34,9 +36,10 @@ def host():
 
 
 def _rand_fq(oracle, curve, n, rng):
-    p = int.from_bytes(oracle.constant(curve, 0).tobytes(), "little")
-    fb = FQ[curve]
-    vals = [int.from_bytes(rng.bytes(fb + 8), "little") % p for _ in range(n)]
+    comps = 2 if curve >= 2 else 1  # Fq2 elements are c0 | c1
+    fb = FQ[curve] // comps
+    p = int.from_bytes(oracle.constant(curve, 0)[:fb].tobytes(), "little")
+    vals = [int.from_bytes(rng.bytes(fb + 8), "little") % p for _ in range(n * comps)]
     # extremes: 0, 1, p-1, all-ones limb patterns below p
     vals[:6] = [0, 1, p - 1, p - 2, (1 << (p.bit_length() - 1)) - 1, (p >> 1)]
     return np.frombuffer(b"".join(v.to_bytes(fb, "little") for v in vals), dtype=np.uint8).copy()
