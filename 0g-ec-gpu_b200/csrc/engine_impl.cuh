@@ -186,6 +186,125 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   return MSM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The three sorts (kernels.cuh).  All leave bucket_start[NB+1] (exclusive scan of the bucket sizes,
+// bucket_start[NB] = number of non-zero digits) and the entries in bucket order.  sg is the geometry
+// of the (sub-)batch, E_max its digit bound; temporaries come from the scratch arena.
+// ---------------------------------------------------------------------------------------------
+struct SortBuffers {
+  uint32_t *counts, *bucket_start, *cursor, *tile_sums, *entries;
+};
+
+inline void enqueue_bucket_scan(cudaStream_t st, const Geometry& g, const SortBuffers& b) {
+  const uint32_t n_tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(b.counts, g.NB, b.bucket_start, b.tile_sums);
+  k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(b.tile_sums, n_tiles, b.tile_sums + n_tiles);
+  k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(b.bucket_start, g.NB, b.tile_sums, b.tile_sums + n_tiles, b.cursor);
+}
+
+// digits staged per k_partition block (8 bytes each in shared memory): measured best of 6144 .. 12288
+inline uint32_t partition_tile(uint32_t W) {
+  uint32_t part_entries = 12288;
+  if (const char* env = getenv("MSM_B200_PART_ENTRIES")) part_entries = (uint32_t)atoi(env);
+  const uint32_t tile = part_entries / W;
+  return tile > 1024 ? 1024 : (tile < 64 ? 64 : tile);
+}
+
+// Binned sort: every per-digit atomic in shared memory (large calls).
+inline int enqueue_sort_binned(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
+                               const uint32_t* scalars, const SortBuffers& b) {
+  cudaStream_t st = dc.stream;
+  CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
+  if (sg.L == 0) {
+    enqueue_bucket_scan(st, sg, b);
+    return MSM_OK;
+  }
+  const size_t cap = pl.E_max / pl.n_sub + sg.W;
+  uint32_t* tmp_g = dc.arena.take<uint32_t>(cap);
+  uint32_t* tmp_v = dc.arena.take<uint32_t>(cap);
+  uint32_t* bin_count = dc.arena.take<uint32_t>(1024);  // [bin_count | bin_cursor]: one memset
+  uint32_t* bin_cursor = dc.arena.take<uint32_t>(1024);
+  uint32_t* bin_start = dc.arena.take<uint32_t>(1025);
+  uint32_t* tile_start = dc.arena.take<uint32_t>(1025);
+  const uint32_t bin_shift = pl.bin_shift;
+  const uint32_t n_bins = (uint32_t)(((uint64_t)sg.NB + (1ull << bin_shift) - 1) >> bin_shift);
+  CU_TRY(ctx, cudaMemsetAsync(bin_count, 0, (size_t)((char*)bin_start - (char*)bin_count), st));
+  launch_bin_count((sg.L + BIN_COUNT_SCALARS - 1) / BIN_COUNT_SCALARS, st, scalars, sg, bin_shift, n_bins, bin_count);
+  k_bin_scan<<<1, SCAN_BLOCK, 0, st>>>(bin_count, n_bins, bin_start, tile_start);
+  const uint32_t tile = partition_tile(sg.W);
+  const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * sg.W) * 4;
+  CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, scalars, sg, tile, bin_shift, n_bins, bin_start, 0u,
+                               bin_cursor, tmp_g, tmp_v));
+  const uint32_t max_tiles = (uint32_t)(E_max / BIN_TILE) + n_bins + 1;
+  k_bin_hist<<<max_tiles, BIN_BLOCK, (size_t)4 << bin_shift, st>>>(tmp_g, bin_start, tile_start, n_bins, bin_shift, sg.NB,
+                                                                  b.counts);
+  enqueue_bucket_scan(st, sg, b);
+  const size_t psmem = bin_place_smem(bin_shift);
+  CU_TRY(ctx, cudaFuncSetAttribute(k_bin_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+  k_bin_place<<<max_tiles, PLACE_BLOCK, psmem, st>>>(tmp_g, tmp_v, bin_start, tile_start, n_bins, bin_shift, sg.NB, b.cursor,
+                                                    b.entries);
+  pl.scatter_passes = 0;
+  dc.launches += 5;
+  return MSM_OK;
+}
+
+// Two-level scatter with global cursor atomics in the second level (MSM_B200_PARTITION=1: measured slower
+// than both other sorts, kept as evidence).
+inline int enqueue_sort_partition(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
+                                  const uint32_t* scalars, const SortBuffers& b) {
+  cudaStream_t st = dc.stream;
+  CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
+  const uint32_t db = 256, dg = (sg.L + db - 1) / db;
+  if (dg) launch_digits<false>(dg, db, st, scalars, sg, b.counts, nullptr, 0u, sg.NB);
+  enqueue_bucket_scan(st, sg, b);
+  if (!dg) return MSM_OK;
+  const size_t cap = pl.E_max / pl.n_sub + sg.W;
+  uint32_t* tmp_g = dc.arena.take<uint32_t>(cap);
+  uint32_t* tmp_v = dc.arena.take<uint32_t>(cap);
+  uint32_t* bin_cursor = dc.arena.take<uint32_t>(4096);
+  uint32_t bins = 16;
+  while (bins < 1024 && (uint64_t)bins * (4u << 20) < E_max * 4) bins <<= 1;  // ~4 MB of entries per bin
+  uint32_t nb_log = 0;
+  while ((1ull << nb_log) < sg.NB) nb_log++;
+  uint32_t bins_log = 0;
+  while ((1u << bins_log) < bins) bins_log++;
+  const uint32_t bin_shift = nb_log > bins_log ? nb_log - bins_log : 0;
+  const uint32_t n_bins = (uint32_t)(((uint64_t)sg.NB + (1ull << bin_shift) - 1) >> bin_shift);
+  const uint32_t tile = partition_tile(sg.W);
+  const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * sg.W) * 4;
+  CU_TRY(ctx, cudaMemsetAsync(bin_cursor, 0, (size_t)n_bins * 4, st));
+  CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, scalars, sg, tile, bin_shift, n_bins, b.bucket_start,
+                               bin_shift, bin_cursor, tmp_g, tmp_v));
+  k_final_scatter<<<(uint32_t)((E_max + 255) / 256), 256, 0, st>>>(tmp_g, tmp_v, b.bucket_start + sg.NB, b.cursor, b.entries);
+  pl.scatter_passes = 0;
+  dc.launches += 2;
+  return MSM_OK;
+}
+
+// Single-level sort: one L2 atomic per digit in the histogram and in the scatter (small calls).  The
+// scatter runs in bucket-range passes: each pass writes a bounded slice of `entries` at random, which the
+// 126 MB L2 partly absorbs; every pass re-reads the scalars (sequential).
+inline int enqueue_sort_atomic(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
+                               const uint32_t* scalars, const SortBuffers& b) {
+  cudaStream_t st = dc.stream;
+  CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
+  const uint32_t db = 256, dg = (sg.L + db - 1) / db;
+  if (dg) launch_digits<false>(dg, db, st, scalars, sg, b.counts, nullptr, 0u, sg.NB);
+  enqueue_bucket_scan(st, sg, b);
+  uint32_t passes = (uint32_t)((E_max * 4 + (200u << 20) - 1) / (200u << 20));
+  if (const char* env = getenv("MSM_B200_SCATTER_PASSES")) passes = (uint32_t)atoi(env);
+  passes = passes < 1 ? 1 : (passes > 8 ? 8 : passes);
+  pl.scatter_passes = passes;
+  const uint32_t per = (sg.NB + passes - 1) / passes;
+  for (uint32_t ps = 0; ps < passes && dg; ps++) {
+    const uint32_t lo = ps * per, hi = lo + per < sg.NB ? lo + per : sg.NB;
+    if (lo >= hi) break;
+    launch_digits<true>(dg, db, st, scalars, sg, b.cursor, b.entries, lo, hi);
+    dc.launches += 1;
+  }
+  return MSM_OK;
+}
+
 // Enqueue one whole MSM batch on dc.stream.  d_scalars / d_out are device pointers.  No sync.
 // pl.n_sub > 1 (single-task calls only): the scalar row is processed in n_sub contiguous
 // sub-batches, each sorted and accumulated as soon as sub_ready[k] has fired (its scalars have
@@ -245,85 +364,12 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     const PackedAffine<F>* bases_sb = (n_sub > 1 && !g.fold) ? d_bases + first : d_bases;
 
     if (sub_ready) CU_TRY(ctx, cudaStreamWaitEvent(st, sub_ready[sb], 0));
-    // --- sort: histogram, scan, scatter
-    CU_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.NB + 1) * 4, st));
-    const uint32_t db = 256, dg = (sg.L + db - 1) / db;
-    if (pl.sort_mode == 2 && dg) {
-      // binned sort (kernels.cuh): every per-digit atomic in shared memory
-      uint32_t* tmp_g = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
-      uint32_t* tmp_v = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
-      uint32_t* bin_count = dc.arena.take<uint32_t>(1024);  // [bin_count | bin_cursor]: one memset
-      uint32_t* bin_cursor = dc.arena.take<uint32_t>(1024);
-      uint32_t* bin_start = dc.arena.take<uint32_t>(1025);
-      uint32_t* tile_start = dc.arena.take<uint32_t>(1025);
-      const uint32_t bin_shift = pl.bin_shift;
-      const uint32_t n_bins = (uint32_t)(((uint64_t)g.NB + (1ull << bin_shift) - 1) >> bin_shift);
-      CU_TRY(ctx, cudaMemsetAsync(bin_count, 0, (size_t)((char*)bin_start - (char*)bin_count), st));
-      launch_bin_count((sg.L + BIN_COUNT_SCALARS - 1) / BIN_COUNT_SCALARS, st, sc_sb, sg, bin_shift, n_bins, bin_count);
-      k_bin_scan<<<1, SCAN_BLOCK, 0, st>>>(bin_count, n_bins, bin_start, tile_start);
-      uint32_t part_entries = 12288;  // digits staged per k_partition block (8 B each in shared memory)
-      if (const char* env = getenv("MSM_B200_PART_ENTRIES")) part_entries = (uint32_t)atoi(env);
-      uint32_t tile = part_entries / g.W;
-      tile = tile > 1024 ? 1024 : (tile < 64 ? 64 : tile);
-      const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * g.W) * 4;
-      CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, sc_sb, sg, tile, bin_shift, n_bins, bin_start, 0u,
-                                   bin_cursor, tmp_g, tmp_v));
-      const uint32_t max_tiles = (uint32_t)(E_max / BIN_TILE) + n_bins + 1;
-      const size_t hsmem = (size_t)4 << bin_shift;
-      k_bin_hist<<<max_tiles, BIN_BLOCK, hsmem, st>>>(tmp_g, bin_start, tile_start, n_bins, bin_shift, g.NB, counts);
-      k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
-      k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
-      k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(bucket_start, g.NB, tile_sums, tile_sums + n_tiles, cursor);
-      const size_t psmem = bin_place_smem(bin_shift);
-      CU_TRY(ctx, cudaFuncSetAttribute(k_bin_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-      k_bin_place<<<max_tiles, PLACE_BLOCK, psmem, st>>>(tmp_g, tmp_v, bin_start, tile_start, n_bins, bin_shift, g.NB,
-                                                        cursor, entries);
-      pl.scatter_passes = 0;
-      dc.launches += 5;
-    } else {
-    if (dg) launch_digits<false>(dg, db, st, sc_sb, sg, counts, nullptr, 0u, g.NB);
-    k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(counts, g.NB, bucket_start, tile_sums);
-    k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(tile_sums, n_tiles, tile_sums + n_tiles);
-    k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(bucket_start, g.NB, tile_sums, tile_sums + n_tiles, cursor);
-    if (pl.partition && dg) {
-      // two-level scatter (kernels.cuh): partition by the high bits of the bucket id, then place
-      uint32_t* tmp_g = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
-      uint32_t* tmp_v = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
-      uint32_t* bin_cursor = dc.arena.take<uint32_t>(4096);
-      uint32_t bins = 16;
-      while (bins < 1024 && (uint64_t)bins * (4u << 20) < E_max * 4) bins <<= 1;  // ~4 MB of entries per bin
-      uint32_t nb_log = 0;
-      while ((1ull << nb_log) < g.NB) nb_log++;
-      uint32_t bins_log = 0;
-      while ((1u << bins_log) < bins) bins_log++;
-      const uint32_t bin_shift = nb_log > bins_log ? nb_log - bins_log : 0;
-      const uint32_t n_bins = (uint32_t)(((uint64_t)g.NB + (1ull << bin_shift) - 1) >> bin_shift);
-      uint32_t tile = 12288 / g.W;
-      tile = tile > 1024 ? 1024 : (tile < 64 ? 64 : tile);
-      const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * g.W) * 4;
-      CU_TRY(ctx, cudaMemsetAsync(bin_cursor, 0, (size_t)n_bins * 4, st));
-      CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, sc_sb, sg, tile, bin_shift, n_bins, bucket_start,
-                                   bin_shift, bin_cursor, tmp_g, tmp_v));
-      k_final_scatter<<<(uint32_t)((E_max + 255) / 256), 256, 0, st>>>(tmp_g, tmp_v, bucket_start + g.NB, cursor, entries);
-      pl.scatter_passes = 0;
-      dc.launches += 2;
-    } else {
-      // scatter in bucket-range passes: each pass writes a bounded slice of `entries` at random,
-      // which the 126 MB L2 partly absorbs; every pass re-reads the scalars (sequential).  Measured
-      // at 2^24: 4 passes best for c = 22 folded, 1-2 for c = 16.
-      uint32_t passes = (uint32_t)((E_max * 4 + (200u << 20) - 1) / (200u << 20));
-      if (const char* env = getenv("MSM_B200_SCATTER_PASSES")) passes = (uint32_t)atoi(env);
-      passes = passes < 1 ? 1 : (passes > 8 ? 8 : passes);
-      pl.scatter_passes = passes;
-      const uint32_t per = (g.NB + passes - 1) / passes;
-      for (uint32_t ps = 0; ps < passes && dg; ps++) {
-        const uint32_t lo = ps * per, hi = lo + per < g.NB ? lo + per : g.NB;
-        if (lo >= hi) break;
-        launch_digits<true>(dg, db, st, sc_sb, sg, cursor, entries, lo, hi);
-        dc.launches += 1;
-      }
-    }
-    }
+    // --- sort: bucket_start[NB+1] and the entries in bucket order
+    const SortBuffers sbuf{counts, bucket_start, cursor, tile_sums, entries};
+    int src = pl.sort_mode == 2 ? enqueue_sort_binned(ctx, dc, pl, sg, E_max, sc_sb, sbuf)
+              : pl.partition   ? enqueue_sort_partition(ctx, dc, pl, sg, E_max, sc_sb, sbuf)
+                               : enqueue_sort_atomic(ctx, dc, pl, sg, E_max, sc_sb, sbuf);
+    if (src != MSM_OK) return src;
     if (timed && sb == 0) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
     if (aborted(ctx)) return MSM_ERR_ABORTED;
     // --- accumulate

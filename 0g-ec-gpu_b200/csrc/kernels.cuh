@@ -3,9 +3,11 @@
 // Pipeline for one call (T = num_chunks scalar-side tasks, W windows of c bits, B = 2^(c-1)
 // buckets per (task, window), `lines` base lines sharing the scalar row):
 //
-//   k_digits<COUNT>   signed-digit (Booth) decomposition of every scalar, histogram of bucket ids
-//   k_scan_*          exclusive scan of the histogram  -> bucket_start[NB+1]
-//   k_digits<SCATTER> same decomposition, scatter (point index | sign) into bucket order
+//   sort              signed-digit (Booth) decomposition of every scalar and a counting sort of the
+//                     (point index | sign) entries by bucket id -> bucket_start[NB+1], entries[]:
+//                       small calls: k_digits<COUNT>, k_scan_*, k_digits<SCATTER> (one L2 atomic per digit)
+//                       large calls: k_bin_count, k_bin_scan, k_partition, k_bin_hist, k_scan_*,
+//                                    k_bin_place (every per-digit atomic in shared memory)
 //   k_accumulate      one thread per fixed-size slice of the sorted entry list; XYZZ mixed adds;
 //                     whole buckets are written directly, buckets cut by a slice boundary go to
 //                     per-slice partial slots
