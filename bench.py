@@ -101,6 +101,16 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons, "window": window}
 
 
+def sampler_extra_steps(ms_total, steps):
+    """Untimed steps to append after a timed region of ms_total milliseconds (max over ranks) so that the
+    clock sampler sees at least ~0.3 s of the same load.  A pure function of values that are identical on
+    every rank (tests/test_sharding_gloo.py pins that property): the step contains a collective."""
+    if ms_total >= 250.0 or steps <= 0:
+        return 0
+    per_step = max(ms_total / steps, 0.05)
+    return min(int(-(-300.0 // per_step)), 2000)
+
+
 def cpu_baseline(curve, log_sample, threads=None):
     """The oracle's multiexp_cpu (restatement of ec-gpu-proxy/src/multiexp_cpu.rs:244-367) on the
     host cores: a reported baseline, not the target."""
@@ -344,17 +354,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        clocks = None
-        if sampler:
-            if t1 - t0 < 0.25:  # keep the same load up until the sampler has seen it
-                while time.perf_counter() - t1 < 0.3:
-                    fn()
-                torch.cuda.synchronize()
-            clocks = sampler.stop(t0, t1)
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), clocks
+        ms = float(ms.item())
+        clocks = None
+        if sampler:
+            # Keep the same load up until nvidia-smi (50 ms period) has seen it.  The step holds a collective
+            # when world > 1, so every rank must run the SAME number of extra steps: the count comes from the
+            # all-reduced time, never from a local clock.
+            for _ in range(sampler_extra_steps(ms, steps)):
+                fn()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            clocks = sampler.stop(t0, t1)
+        return ms, clocks
 
     launches0 = None
     # warm-up happens inside timed(); launches are counted over the timed steps only

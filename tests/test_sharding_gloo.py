@@ -65,3 +65,53 @@ def test_shard_ranges_cover_exactly(engine):
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(e - s for s, e in spans) == engine.chunk_size(n, parts) or n == 0
+
+
+def _timed_loop_worker(rank, world, port, out_dir):
+    """The collective structure of bench.py's timed(): K steps that each hold an all-gather, the
+    all-reduced time, then the extra steps of the clock sampler -- with rank-dependent step times."""
+    import time
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+
+    calls = 0
+    mine, gathered = torch.full((4,), rank, dtype=torch.uint8), torch.zeros(4 * world, dtype=torch.uint8)
+
+    def step():
+        nonlocal calls
+        time.sleep(0.001 * (1 + 3 * rank))  # ranks run at different speeds
+        dist.all_gather_into_tensor(gathered, mine)
+        calls += 1
+
+    steps = 5
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    extra = bench.sampler_extra_steps(float(ms.item()), steps)
+    for _ in range(min(extra, 40)):  # same clamp on every rank
+        step()
+    dist.barrier()
+    np.save(os.path.join(out_dir, "calls%d.npy" % rank), np.array([calls, extra]))
+    dist.destroy_process_group()
+
+
+def test_bench_extra_steps_are_rank_uniform(tmp_path):
+    """bench.py keeps the load up after a short timed region so that the clock sampler sees it; the step
+    contains a collective, so the number of extra steps must be the same on every rank (a count taken
+    from a local clock deadlocks NCCL at N = 8)."""
+    import bench
+
+    assert bench.sampler_extra_steps(300.0, 5) == 0
+    assert bench.sampler_extra_steps(28.0, 5) == 54      # N = 8: 5 steps of 5.6 ms
+    assert bench.sampler_extra_steps(0.0, 5) == 2000 and bench.sampler_extra_steps(10.0, 0) == 0
+    world = 2
+    mp.spawn(_timed_loop_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = np.load(tmp_path / "calls0.npy"), np.load(tmp_path / "calls1.npy")
+    assert (a == b).all() and a[0] > 5
