@@ -359,7 +359,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms = float(ms.item())
         clocks = None
-        if sampler:
+        if sampler is not None:  # every rank passes one (rank-uniform branch: it holds collectives)
             # Keep the same load up until nvidia-smi (50 ms period) has seen it.  The step holds a collective
             # when world > 1, so every rank must run the SAME number of extra steps: the count comes from the
             # all-reduced time, never from a local clock.
