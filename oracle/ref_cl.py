@@ -28,6 +28,8 @@ def lib(curve: int):
         l.ref_fq_op.argtypes = [i32, vp, vp, vp, sz]
         l.ref_ec_op.argtypes = [i32, vp, vp, vp, sz]
         l.ref_multiple_multiexp.argtypes = [vp, sz, vp, sz, u32, u32, i32, vp]
+        l.ref_fr_fft.argtypes = [vp, vp, u32]
+        l.ref_ec_fft.argtypes = [vp, vp, u32]
         _libs[curve] = l
     return _libs[curve]
 
@@ -63,4 +65,29 @@ def multiple_multiexp(curve, bases, exps, num_chunks, window_size, neg_is_cheap)
     rc = lib(curve).ref_multiple_multiexp(bases.ctypes.data, n_bases, exps.ctypes.data, L, num_chunks,
                                           window_size, 1 if neg_is_cheap else 0, out.ctypes.data)
     assert rc == 0
+    return out
+
+
+def fr_fft(curve, elems_mont, omega_mont):
+    """The reference's FIELD_radix_fft kernel (ag-build/cl/fft.cl:4-66) under the pass loop of
+    SingleFftKernel::radix_fft (ec-gpu-proxy/src/fft.rs:50-136).  Returns the transformed copy."""
+    out = np.ascontiguousarray(elems_mont, dtype=np.uint8).copy()
+    n = out.size // 32
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    om = np.ascontiguousarray(omega_mont, dtype=np.uint8)
+    assert lib(curve).ref_fr_fft(out.ctypes.data, om.ctypes.data, log_n) == 0
+    return out
+
+
+def ec_fft(curve, jac, omegas_mont):
+    """The reference's POINT_radix_fft kernel (ag-build/cl/ec-fft.cl:4-76) under the pass loop of
+    ag_cuda_ec::ec_fft::radix_ec_fft (ag-cuda-ec/src/ec_fft.rs:13-99).  omegas_mont: [32, 32]."""
+    out = np.ascontiguousarray(jac, dtype=np.uint8).copy()
+    n = out.size // (3 * _FQ[curve])
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    om = np.ascontiguousarray(omegas_mont, dtype=np.uint8)
+    assert om.size == 32 * 32
+    assert lib(curve).ref_ec_fft(out.ctypes.data, om.ctypes.data, log_n) == 0
     return out

@@ -11,6 +11,7 @@
 
   ec_fft_vectors.json  from oracle/pyref.py: the DFT of G1 points evaluated by its definition.
   fr_fft_vectors.json  the DFT over the scalar field evaluated by its definition (Python integers).
+  ref_cl_fft_vectors.json  outputs of the reference's own fft.cl / ec-fft.cl kernels run on the host (needs /root/reference).
   g2_vectors.json      G2 over Fq2 from oracle/pyref.py's G2Params (--only-g2 regenerates just this file).
 
 Run from the repo root:  python tests/golden/make_golden.py   (--only-fft: just the FFT files)
@@ -253,6 +254,46 @@ def make_g2():
         json.dump(out, f, indent=1)
 
 
+def make_ref_cl_fft():
+    """ref_cl_fft_vectors.json: outputs of the REFERENCE'S OWN FFT kernels (ag-build/cl/fft.cl,
+    ag-build/cl/ec-fft.cl) executed on the host by oracle/build_ref.py under restatements of their host
+    pass loops (ec-gpu-proxy/src/fft.rs:50-136, ag-cuda-ec/src/ec_fft.rs:13-99).  Needs /root/reference."""
+    from oracle import oracle as O
+    from oracle import ref_cl as R
+
+    if not os.path.isdir("/root/reference/ag-build/cl"):
+        print("reference sources absent: ref_cl_fft_vectors.json not regenerated")
+        return
+    out = {"generator": "tests/golden/make_golden.py make_ref_cl_fft (oracle/_ref: the reference's fft.cl / ec-fft.cl on the host)",
+           "curves": {}}
+    for curve, name, g in ((0, "bn254", 5), (1, "bls12_381", 7)):
+        cv = P.CURVES[curve]
+        fq = O.FQ_BYTES[curve]
+        c = {"fr_fft": [], "ec_fft": []}
+        for log_n in (3, 9):   # 9 > MAX_LOG2_RADIX = 8: two passes of the reference kernel
+            n = 1 << log_n
+            omega = pow(g, (cv.r - 1) // n, cv.r)
+            om = np.frombuffer((omega * (1 << 256) % cv.r).to_bytes(32, "little"), dtype=np.uint8).copy()
+            a = O.gen_scalars(curve, SEED + log_n, n)
+            c["fr_fft"].append({"log_n": log_n, "omega_mont": hx(om), "input_mont": hx(a), "output_mont": hx(R.fr_fft(curve, a, om))})
+        for log_n in (2, 5):
+            n = 1 << log_n
+            omega = pow(g, (cv.r - 1) // n, cv.r)
+            oms = np.zeros((32, 32), dtype=np.uint8)
+            for i in range(32):
+                oms[i] = np.frombuffer((pow(omega, 1 << i, cv.r) * (1 << 256) % cv.r).to_bytes(32, "little"), dtype=np.uint8)
+            jac = np.zeros((n, 3 * fq), dtype=np.uint8)
+            jac[:, :2 * fq] = O.gen_points(curve, SEED + 7 + log_n, n)
+            jac[:, 2 * fq:] = O.constant(curve, 1)
+            res = R.ec_fft(curve, jac, oms)
+            xy, inf = O.to_affine(curve, res)  # the Jacobian representative is the reference's; the fixture keeps the group elements
+            c["ec_fft"].append({"log_n": log_n, "omegas_mont": hx(oms), "input_jacobian": hx(jac),
+                                "output_affine_canonical": hx(xy), "output_is_inf": [int(v) for v in inf]})
+        out["curves"][name] = c
+    with open(os.path.join(HERE, "ref_cl_fft_vectors.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
     if "--only-ec-fft" not in sys.argv and "--only-fft" not in sys.argv and "--only-g2" not in sys.argv:
         make_pyref()
@@ -260,7 +301,8 @@ if __name__ == "__main__":
     if "--only-g2" not in sys.argv:
         make_ec_fft()
         make_fr_fft()
+        make_ref_cl_fft()
     if "--only-fft" not in sys.argv:
         make_g2()
-    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json", "fr_fft_vectors.json", "g2_vectors.json"):
+    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json", "fr_fft_vectors.json", "ref_cl_fft_vectors.json", "g2_vectors.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")

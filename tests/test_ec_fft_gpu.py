@@ -129,3 +129,18 @@ def test_ec_fft_and_fft_in_concurrent_threads(engine, oracle, pyref):
     assert not errs, errs
     for t in range(4):
         assert_same_points(oracle, curve, inputs[t], want[t], f"thread {t}")
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_ec_fft_vs_reference_kernel_fixture(engine, oracle, ws, curve):
+    """Same group elements as the reference's own POINT_radix_fft kernel (ag-build/cl/ec-fft.cl) run on the
+    host under the pass loop of radix_ec_fft (tests/golden/ref_cl_fft_vectors.json)."""
+    with open(os.path.join(HERE, "golden", "ref_cl_fft_vectors.json")) as f:
+        cases = json.load(f)["curves"][NAMES[curve]]["ec_fft"]
+    for case in cases:
+        jac = np.frombuffer(bytes.fromhex(case["input_jacobian"]), dtype=np.uint8).reshape(-1, 3 * FQ[curve]).copy()
+        omegas = np.frombuffer(bytes.fromhex(case["omegas_mont"]), dtype=np.uint8).reshape(-1, 32).copy()
+        engine.radix_ec_fft(ws[curve], jac, omegas)
+        xy, inf = oracle.to_affine(curve, jac)
+        assert xy.tobytes().hex() == case["output_affine_canonical"], case["log_n"]
+        assert [int(v) for v in inf] == case["output_is_inf"]

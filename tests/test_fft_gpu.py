@@ -83,3 +83,16 @@ def test_fr_fft_many_and_errors(engine, kernels, oracle, pyref):
     aborting = engine.FftKernel.create_with_abort([0], lambda: True, 0)
     with pytest.raises(engine.EcErrorAborted):
         aborting.radix_fft(ins[0], oms[0], 3)
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_fr_fft_vs_reference_kernel_fixture(kernels, curve):
+    """Bit-exact against outputs of the reference's own FIELD_radix_fft kernel (ag-build/cl/fft.cl) run on
+    the host (tests/golden/ref_cl_fft_vectors.json, made by tests/golden/make_golden.py)."""
+    with open(os.path.join(HERE, "golden", "ref_cl_fft_vectors.json")) as f:
+        cases = json.load(f)["curves"][NAMES[curve]]["fr_fft"]
+    for case in cases:
+        a = np.frombuffer(bytes.fromhex(case["input_mont"]), dtype=np.uint8).reshape(-1, 32).copy()
+        om = np.frombuffer(bytes.fromhex(case["omega_mont"]), dtype=np.uint8).copy()
+        kernels[curve].radix_fft(a, om, case["log_n"])
+        assert a.tobytes().hex() == case["output_mont"], case["log_n"]

@@ -239,3 +239,46 @@ def test_fr_fft_oracle_vs_naive_dft_golden(oracle, curve):
         want = _b(case["output_mont"], 32)
         got = oracle.fr_fft(curve, a, _b(case["omega_mont"], 32)[0])
         assert (got == want).all(), f"log_n={case['log_n']}"
+
+
+# ---------------------------------------------------------------------------------------------
+# FFT / EC-FFT against the REFERENCE'S OWN kernels (ag-build/cl/fft.cl, ag-build/cl/ec-fft.cl) run on the
+# host by oracle/build_ref.py under restatements of their host pass loops (ec-gpu-proxy/src/fft.rs:50-136,
+# ag-cuda-ec/src/ec_fft.rs:13-99): committed fixture, and live when /root/reference is present.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", [0, 1])
+def test_fft_oracle_vs_reference_cl_fixture(oracle, curve):
+    g = _load("ref_cl_fft_vectors.json")["curves"][NAMES[curve]]
+    for case in g["fr_fft"]:
+        got = oracle.fr_fft(curve, _b(case["input_mont"], 32), _b(case["omega_mont"], 32)[0])
+        assert got.tobytes().hex() == case["output_mont"], f"fr_fft 2^{case['log_n']}"
+    for case in g["ec_fft"]:
+        jac = _b(case["input_jacobian"], 3 * FQ[curve])
+        got = oracle.ec_fft(curve, jac, _b(case["omegas_mont"], 32)[0])
+        xy, inf = oracle.to_affine(curve, got)
+        assert xy.tobytes().hex() == case["output_affine_canonical"] and [int(v) for v in inf] == case["output_is_inf"]
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_fft_oracle_vs_reference_cl_live(oracle, pyref, curve):
+    from oracle import ref_cl
+
+    if not ref_cl.available():
+        pytest.skip("reference sources not present (GPU box): the committed fixture covers this")
+    cv = pyref.CURVES[curve]
+    gen = {0: 5, 1: 7}[curve]
+    for log_n in (1, 4, 8, 10):  # 10: two passes (8 + 2 rounds) of the reference kernel
+        n = 1 << log_n
+        om = np.frombuffer((pow(gen, (cv.r - 1) // n, cv.r) * (1 << 256) % cv.r).to_bytes(32, "little"), dtype=np.uint8).copy()
+        a = oracle.gen_scalars(curve, 600 + log_n, n)
+        assert (ref_cl.fr_fft(curve, a, om) == oracle.fr_fft(curve, a, om)).all(), f"fr_fft 2^{log_n}"
+    for log_n in (1, 3, 6):
+        n = 1 << log_n
+        omega = pow(gen, (cv.r - 1) // n, cv.r)
+        oms = np.zeros((32, 32), dtype=np.uint8)
+        for i in range(32):
+            oms[i] = np.frombuffer((pow(omega, 1 << i, cv.r) * (1 << 256) % cv.r).to_bytes(32, "little"), dtype=np.uint8)
+        jac = np.zeros((n, 3 * FQ[curve]), dtype=np.uint8)
+        jac[:, :2 * FQ[curve]] = oracle.gen_points(curve, 700 + log_n, n)
+        jac[:, 2 * FQ[curve]:] = oracle.constant(curve, 1)
+        assert_same_points(oracle, curve, ref_cl.ec_fft(curve, jac, oms), oracle.ec_fft(curve, jac, oms[0]), f"ec_fft 2^{log_n}")
