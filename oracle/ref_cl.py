@@ -29,6 +29,9 @@ def lib(curve: int):
         l.ref_ec_op.argtypes = [i32, vp, vp, vp, sz]
         l.ref_multiple_multiexp.argtypes = [vp, sz, vp, sz, u32, u32, i32, vp]
         l.ref_fr_fft.argtypes = [vp, vp, u32]
+        l.ref_fq2_op.argtypes = [i32, vp, vp, vp, sz]
+        l.ref_g2_ec_op.argtypes = [i32, vp, vp, vp, sz]
+        l.ref_g2_multiple_multiexp.argtypes = [vp, sz, vp, sz, u32, u32, i32, vp]
         l.ref_ec_fft.argtypes = [vp, vp, u32]
         _libs[curve] = l
     return _libs[curve]
@@ -90,4 +93,35 @@ def ec_fft(curve, jac, omegas_mont):
     om = np.ascontiguousarray(omegas_mont, dtype=np.uint8)
     assert om.size == 32 * 32
     assert lib(curve).ref_ec_fft(out.ctypes.data, om.ctypes.data, log_n) == 0
+    return out
+
+
+# ---- G2: the reference's field2.cl / ec.cl / multiexp.cl instantiated over Fq2 the way its SourceBuilder
+# would (ag-build/src/source/synthesis.rs:100-110); `curve` is the G1 id (0 / 1) of the same pairing suite.
+def fq2_op(curve, op, a, b=None):
+    """op: 0 add 1 sub 2 mul 3 sqr 4 double (FIELD2_* of ag-build/cl/field2.cl)."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    bb = a if b is None else np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.zeros_like(a)
+    assert lib(curve).ref_fq2_op(op, a.ctypes.data, bb.ctypes.data, out.ctypes.data, a.size // (2 * _FQ[curve])) == 0
+    return out
+
+
+def g2_ec_op(curve, op, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    out = np.zeros_like(a)
+    bp = None if b is None else np.ascontiguousarray(b, dtype=np.uint8).ctypes.data
+    assert lib(curve).ref_g2_ec_op(op, a.ctypes.data, bp, out.ctypes.data, a.size // (6 * _FQ[curve])) == 0
+    return out
+
+
+def g2_multiple_multiexp(curve, bases, exps, num_chunks, window_size, neg_is_cheap):
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    exps = np.ascontiguousarray(exps, dtype=np.uint8)
+    L = exps.size // 32
+    n_bases = bases.size // (4 * _FQ[curve])
+    out = np.zeros(((n_bases // L) * num_chunks, 6 * _FQ[curve]), dtype=np.uint8)
+    rc = lib(curve).ref_g2_multiple_multiexp(bases.ctypes.data, n_bases, exps.ctypes.data, L, num_chunks,
+                                             window_size, 1 if neg_is_cheap else 0, out.ctypes.data)
+    assert rc == 0
     return out

@@ -12,6 +12,7 @@
   ec_fft_vectors.json  from oracle/pyref.py: the DFT of G1 points evaluated by its definition.
   fr_fft_vectors.json  the DFT over the scalar field evaluated by its definition (Python integers).
   ref_cl_fft_vectors.json  outputs of the reference's own fft.cl / ec-fft.cl kernels run on the host (needs /root/reference).
+  ref_cl_g2_vectors.json   the reference's field2.cl / ec.cl / multiexp.cl instantiated over Fq2, run on the host.
   g2_vectors.json      G2 over Fq2 from oracle/pyref.py's G2Params (--only-g2 regenerates just this file).
 
 Run from the repo root:  python tests/golden/make_golden.py   (--only-fft: just the FFT files)
@@ -294,6 +295,48 @@ def make_ref_cl_fft():
         json.dump(out, f, indent=1)
 
 
+def make_ref_cl_g2():
+    """ref_cl_g2_vectors.json: outputs of the REFERENCE'S OWN field2.cl / ec.cl / multiexp.cl instantiated over
+    Fq2 exactly as its SourceBuilder would (ag-build/src/source/synthesis.rs:100-110) and run on the host by
+    oracle/build_ref.py: FIELD2 products, G2 double / add / mixed add, and the POINT_multiexp kernel."""
+    from oracle import oracle as O
+    from oracle import ref_cl as R
+
+    if not os.path.isdir("/root/reference/ag-build/cl"):
+        print("reference sources absent: ref_cl_g2_vectors.json not regenerated")
+        return
+    out = {"generator": "tests/golden/make_golden.py make_ref_cl_g2 (oracle/_ref: the reference's field2.cl / ec.cl / multiexp.cl over Fq2)",
+           "curves": {}}
+    for g1, g2, name in ((0, 2, "bn254_g2"), (1, 3, "bls12_381_g2")):
+        fq = O.FQ_BYTES[g2]
+        rng = np.random.default_rng(500 + g2)
+        p = int.from_bytes(O.constant(g2, 0)[: fq // 2].tobytes(), "little")
+        n = 8
+        mk = lambda: np.frombuffer(b"".join((int.from_bytes(rng.bytes(fq), "little") % p).to_bytes(fq // 2, "little")  # noqa: E731
+                                            for _ in range(2 * n)), dtype=np.uint8).reshape(n, fq).copy()
+        a, b = mk(), mk()
+        c = {"fq2": {"a": hx(a), "b": hx(b), "ops": {nm: hx(R.fq2_op(g1, op, a, b))
+                                                      for op, nm in enumerate(["add", "sub", "mul", "sqr", "double"])}}}
+        pts = O.gen_points(g2, 21, 2 * n)
+        lifted = np.zeros((n, 3 * fq), dtype=np.uint8)
+        lifted[:, :2 * fq] = pts[:n]
+        lifted[:, 2 * fq:] = O.constant(g2, 1)
+        dbl = R.g2_ec_op(g1, 2, lifted)
+        c["ec"] = {"affine": hx(pts), "double": hx(dbl), "double_plus_affine": hx(R.g2_ec_op(g1, 1, dbl, pts[n:]))}
+        L, lines, chunks = 32, 2, 4
+        sc = O.gen_scalars(g2, SEED + 5, L)
+        bp = O.gen_points(g2, SEED + 5, L * lines)
+        c["multiexp"] = {"L": L, "lines": lines, "chunks": chunks, "scalars": hx(sc), "points_mont": hx(bp), "runs": []}
+        for w, neg in ((3, True), (5, False)):
+            res = R.g2_multiple_multiexp(g1, bp, sc, chunks, w, neg)
+            xy, inf = O.to_affine(g2, res)
+            c["multiexp"]["runs"].append({"window_size": w, "neg_is_cheap": neg, "results_affine_canonical": hx(xy),
+                                          "results_is_inf": [int(v) for v in inf]})
+        out["curves"][name] = c
+    with open(os.path.join(HERE, "ref_cl_g2_vectors.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
     if "--only-ec-fft" not in sys.argv and "--only-fft" not in sys.argv and "--only-g2" not in sys.argv:
         make_pyref()
@@ -304,5 +347,6 @@ if __name__ == "__main__":
         make_ref_cl_fft()
     if "--only-fft" not in sys.argv:
         make_g2()
-    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json", "fr_fft_vectors.json", "ref_cl_fft_vectors.json", "g2_vectors.json"):
+        make_ref_cl_g2()
+    for fn in ("pyref_vectors.json", "ref_cl_vectors.json", "ec_fft_vectors.json", "fr_fft_vectors.json", "ref_cl_fft_vectors.json", "g2_vectors.json", "ref_cl_g2_vectors.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
