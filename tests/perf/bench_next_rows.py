@@ -4,7 +4,10 @@ the EC-FFT and the scalar-field FFT -- device time (CUDA events inside the engin
 through the reference-facing call with host buffers, the oracle's CPU restatement on a bounded sample
 of the same workload, and the fraction of the IMAD roofline.  One JSON line per workload.
 
-  python tools/bench_next_rows.py [batched] [amt] [ecfft] [fft]
+  python tests/perf/bench_next_rows.py [batched] [amt] [ecfft] [fft]
+
+Lives under tests/ because it uses the oracle (as the checker and as the CPU baseline), which only tests/,
+__graft_entry__.smoke() and bench.py may do.
 """
 import ctypes
 import json
@@ -14,7 +17,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import ec_gpu_b200 as m  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (CPU baseline legs only)
