@@ -265,7 +265,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a collective that cannot complete should fail the run in minutes, not hold 8 GPUs for NCCL's default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     curve = args.curve
     fq = m.fq_bytes(curve)
     ws = m.Workspace(curve, devices=[local_rank])
