@@ -462,7 +462,8 @@ def main():
             "paths_agree": same,
         }
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(curve, min(args.cpu_log_sample, args.log_n))
+            if world == 1:  # the CPU baseline is reported at N = 1 only (it does not depend on N)
+                out["cpu_baseline"] = cpu_baseline(curve, min(args.cpu_log_sample, args.log_n))
             out["spot_check_vs_oracle"] = spot_check(m, curve, local_rank)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
