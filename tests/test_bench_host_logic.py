@@ -1,0 +1,27 @@
+"""bench.py's host logic without a GPU: the whole main() of the N = 1 path runs against a fake torch.cuda and a
+fake engine in a subprocess (tests/perf/bench_dry_run.py), for the headline and the batched workload; the JSON
+line must carry every key of the bench contract."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_bench_main_dry_run():
+    r = subprocess.run([sys.executable, os.path.join(HERE, "perf", "bench_dry_run.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK [") == 2, r.stdout[-2000:]
+
+
+def test_reference_arm_runs_on_cpu():
+    """bench.py --impl reference: the CPU arm prints the contract line and exits 0 (bounded sample)."""
+    import json
+
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(HERE), "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--ref-log-sample", "12"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
