@@ -9,10 +9,12 @@ import torch
 
 # ---- fake torch.cuda
 class FakeStream: cuda_stream = 0
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
 class FakeEvent:
     def __init__(self, enable_timing=False): pass
     def record(self, stream=None): pass
-    def elapsed_time(self, other): return 12.5
+    def elapsed_time(self, other): return 12.5 + 7.0 * RANK  # ranks disagree until the all-reduce
 torch.cuda.set_device = lambda d: None
 torch.cuda.current_stream = lambda: FakeStream()
 torch.cuda.Event = FakeEvent
@@ -29,6 +31,11 @@ for name in ("empty", "zeros"):
     setattr(torch, name, wrap)
 _real_tensor = torch.tensor
 torch.tensor = lambda *a, **k: _real_tensor(*a, **{kk: vv for kk, vv in k.items() if kk != "device"} )
+
+if WORLD > 1:  # N > 1 control flow on the CPU: gloo stands in for NCCL
+    import torch.distributed as dist
+    _real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, **k: _real_init("gloo", rank=RANK, world_size=WORLD)
 
 # ---- fake engine module
 class FakeLib:
@@ -66,8 +73,10 @@ sys.modules["ec_gpu_b200"] = fake
 
 import bench
 bench.ClockSampler.start = lambda self: setattr(self, "proc", None)
-for argv in (["bench.py", "--log-n", "12", "--steps", "2", "--warmup", "1", "--cpu-log-sample", "12"],
-             ["bench.py", "--workload", "batched", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"]):
+RUNS = ([["bench.py", "--gpus", str(WORLD), "--log-n", "12", "--steps", "2", "--warmup", "1"]] if WORLD > 1 else
+        [["bench.py", "--log-n", "12", "--steps", "2", "--warmup", "1", "--cpu-log-sample", "12"],
+         ["bench.py", "--workload", "batched", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"]])
+for argv in RUNS:
     sys.argv = argv
     r, w = os.pipe()
     saved = os.dup(1)
@@ -77,6 +86,9 @@ for argv in (["bench.py", "--log-n", "12", "--steps", "2", "--warmup", "1", "--c
     finally:
         os.dup2(saved, 1)
         os.close(w)
+    if RANK != 0:  # other ranks print nothing (and bench keeps a dup of the write end open: a read would block)
+        os.close(r)
+        continue
     out = os.read(r, 1 << 20).decode()
     line = [l for l in out.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)

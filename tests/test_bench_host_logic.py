@@ -25,3 +25,20 @@ def test_reference_arm_runs_on_cpu():
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+
+
+def test_bench_two_rank_control_flow_on_gloo():
+    """The N > 1 control flow of bench.py (barriers, all-gather inside every step, all-reduced time, the clock
+    sampler's extra steps) with two CPU ranks whose local timings disagree: must finish -- the version that took
+    the extra-step count from a local clock dead-locked NCCL at N = 8."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "perf", "bench_dry_run.py")],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("OK [") == 1, r.stdout[-2000:]
