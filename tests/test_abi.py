@@ -58,3 +58,55 @@ def test_missing_library_is_an_import_error(tmp_path, monkeypatch):
     monkeypatch.setattr(L, "_LIB", str(tmp_path / "libmsm_b200.so"))
     with pytest.raises(ImportError, match="no CPU fallback"):
         L.load_library()
+
+
+def _header_prototypes():
+    """name -> number of parameters, parsed from include/msm_b200.h"""
+    import re
+
+    text = open(os.path.join(ROOT, "include", "msm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(msm_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_ctypes_table_matches_header():
+    """Every prototype of the header has a ctypes signature with the same number of parameters (a drifted
+    binding would pass garbage through the ABI)."""
+    import inspect
+    import re
+
+    L = importlib.import_module("0g-ec-gpu_b200._lib")
+    protos = _header_prototypes()
+    src = inspect.getsource(L.load_library)
+    table = {}
+    for m in re.finditer(r'"(msm_[a-z0-9_]+)":\s*\(\[(.*?)\],\s*[^\n]+\),?\n', src, flags=re.S):
+        inner = m.group(2).strip()
+        # arguments are comma-separated at bracket depth 0
+        depth, n = 0, 1 if inner else 0
+        for ch in inner:
+            depth += ch in "([" 
+            depth -= ch in ")]"
+            n += ch == "," and depth == 0
+        table[m.group(1)] = n
+    missing = sorted(set(protos) - set(table))
+    assert not missing, f"no ctypes signature for {missing}"
+    wrong = {k: (protos[k], table[k]) for k in protos if protos[k] != table[k]}
+    assert not wrong, f"parameter counts differ (header, ctypes): {wrong}"
+
+
+def test_rust_ffi_declarations_match_header():
+    """rust/msm-b200-sys declares a subset of the header with the same parameter counts."""
+    import re
+
+    protos = _header_prototypes()
+    text = open(os.path.join(ROOT, "rust", "msm-b200-sys", "src", "lib.rs")).read()
+    decls = re.findall(r"pub fn (msm_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]+)?;", text, flags=re.S)
+    assert len(decls) >= 15
+    for name, args in decls:
+        assert name in protos, name
+        n = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
+        assert n == protos[name], (name, n, protos[name])
