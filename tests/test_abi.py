@@ -110,3 +110,24 @@ def test_rust_ffi_declarations_match_header():
         assert name in protos, name
         n = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
         assert n == protos[name], (name, n, protos[name])
+
+
+def test_header_is_valid_c99_and_cpp(tmp_path):
+    """The boundary is a C ABI: the header must compile as plain C (cgo / bindgen / a C caller) and as C++,
+    and a C translation unit that calls through it must link against the library."""
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "msm_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    src = tmp_path / "caller.c"
+    src.write_text('#include "msm_b200.h"\n#include <stdio.h>\n'
+                   "int main(void) { msm_ctx* c = 0; int rc = msm_ctx_create(MSM_CURVE_BN254_G1, 0, 1, &c);\n"
+                   '  printf("%s rc=%d devices=%d\\n", msm_version(), rc, msm_device_count());\n'
+                   "  if (rc == MSM_OK) msm_ctx_destroy(c); return 0; }\n")
+    exe = tmp_path / "caller"
+    so_dir = os.path.join(ROOT, "0g-ec-gpu_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", so_dir, "-lmsm_b200", "-Wl,-rpath," + so_dir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "msm_b200" in out.stdout, out.stdout + out.stderr
