@@ -23,6 +23,13 @@ device.  Total work is fixed => "scaling": "strong".
 Timing: CUDA events on the stream every kernel is launched on (the engine is switched onto torch's
 current stream), barrier + synchronize on both sides, max over ranks.  Inputs per step (1 GiB of
 bases, 0.5 GiB of scalars, >= 0.8 GiB of sorted digits) exceed the 126 MB L2 many times over.
+Clocks: nvidia-smi sampled every 50 ms from before the warm-up; when the timed region is shorter than
+that, the same step keeps running for ~0.3 s after it -- the SAME number of extra steps on every rank
+(sampler_extra_steps: a function of the all-reduced time), because a step holds a collective.
+
+  --workload batched   BASELINE.json configs[4]: 1024 BN254 MSMs of 2^12 points (chunked window table),
+                       tasks split over the ranks, results all-gathered, nothing to add up
+  --curve 1 --log-n 22 BASELINE.json configs[3]: BLS12-381 G1
 """
 import argparse
 import ctypes
