@@ -121,6 +121,7 @@ def load_library() -> ctypes.CDLL:
         "msm_bases_precompute": ([vp, vp, u32], i32),
         "msm_bases_precompute_chunked": ([vp, vp, sz], i32),
         "msm_bases_table_window": ([vp], u32),
+        "msm_bases_set_table_policy": ([vp, vp, i32], i32),
         "msm_bases_size_bytes": ([vp], sz),
         "msm_bases_num_points": ([vp], sz),
         "msm_bases_free": ([vp], i32),

@@ -50,19 +50,51 @@ const FieldOps* pick_ops(int curve) {
   // selects the alternatives that were built and measured:
   //   sat32  canonical values, conditional subtraction after every product
   //   u29    BN254 only: nine 29-bit limbs, carry-free IMAD.WIDE (slower on B200)
-  const char* env = getenv("MSM_B200_FIELD");
-  const bool want_sat = env && (strcmp(env, "sat32") == 0 || strcmp(env, "sat") == 0);
   if (curve == MSM_CURVE_BN254_G2) return field_ops_bn254_g2();
   if (curve == MSM_CURVE_BLS12_381_G2) return field_ops_bls381_g2();
-  if (curve == MSM_CURVE_BLS12_381_G1) return want_sat ? field_ops_bls381_sat() : field_ops_bls381_lazy();
-  if (env && strcmp(env, "u29") == 0) return field_ops_bn254_u29();
-  return want_sat ? field_ops_bn254_sat() : field_ops_bn254_lazy();
+#ifdef MSM_EXPERIMENTAL  // make MSM_EXPERIMENTAL=1: the measured-slower variants are not in the product build
+  const char* env = getenv("MSM_B200_FIELD");
+  const bool want_sat = env && (strcmp(env, "sat32") == 0 || strcmp(env, "sat") == 0);
+  if (curve == MSM_CURVE_BLS12_381_G1 && want_sat) return field_ops_bls381_sat();
+  if (curve == MSM_CURVE_BN254_G1 && env && strcmp(env, "u29") == 0) return field_ops_bn254_u29();
+  if (curve == MSM_CURVE_BN254_G1 && want_sat) return field_ops_bn254_sat();
+#endif
+  return curve == MSM_CURVE_BLS12_381_G1 ? field_ops_bls381_lazy() : field_ops_bn254_lazy();
 }
 
-#define LOCK_OR_BUSY(ctx)            \
-  if (!(ctx)) return MSM_ERR_INVALID; \
-  CtxLock _lock(ctx);                \
+#define LOCK_OR_BUSY(ctx)                                   \
+  if (!(ctx) || (ctx)->closed.load()) return MSM_ERR_INVALID; \
+  CtxLock _lock(ctx);                                       \
   if (!_lock.ok) return MSM_ERR_BUSY
+
+int default_table_policy() {
+  const char* env = getenv("MSM_B200_TABLE");
+  if (!env) return MSM_TABLE_LAZY;
+  if (strcmp(env, "off") == 0 || strcmp(env, "0") == 0) return MSM_TABLE_OFF;
+  if (strcmp(env, "eager") == 0) return MSM_TABLE_EAGER;
+  return MSM_TABLE_LAZY;
+}
+
+// frees the device side of a context; called when the last reference (handle or msm_bases) goes
+void ctx_teardown(msm_ctx* ctx) {
+  for (auto& dc : ctx->devs) {
+    cudaSetDevice(dc.dev);
+    if (dc.stream) cudaStreamSynchronize(dc.stream);
+    dc.arena.release();
+    dc.io.release();
+    if (dc.small) cudaFree(dc.small);
+    if (dc.copy_stream) cudaStreamDestroy(dc.copy_stream);
+    for (auto& e : dc.ev_copy)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : dc.ev)
+      if (e) cudaEventDestroy(e);
+    if (dc.stream && dc.owns_stream) cudaStreamDestroy(dc.stream);
+  }
+  delete ctx;
+}
+void ctx_unref(msm_ctx* ctx) {
+  if (ctx->refs.fetch_sub(1) == 1) ctx_teardown(ctx);
+}
 
 }  // namespace
 
@@ -164,6 +196,11 @@ int msm_ctx_create(int curve, const int* device_ids, int n_devices, msm_ctx** ou
     DeviceCtx dc;
     dc.dev = dev;
     cudaError_t e = cudaSetDevice(dev);
+    if (const char* env = getenv("MSM_B200_L2_FETCH")) {
+      // experiment: L2 fetch granularity for the 64-byte point gathers (32 / 64 / 128 bytes)
+      cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env));
+      cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking);
     for (int k = 0; k < 5 && e == cudaSuccess; k++) e = cudaEventCreate(&dc.ev[k]);
     if (e == cudaSuccess) e = cudaMalloc(&dc.small, 65536);
@@ -200,21 +237,16 @@ int msm_ctx_create(int curve, const int* device_ids, int n_devices, msm_ctx** ou
 }
 
 int msm_ctx_destroy(msm_ctx* ctx) {
-  if (!ctx) return MSM_ERR_INVALID;
-  for (auto& dc : ctx->devs) {
-    cudaSetDevice(dc.dev);
-    if (dc.stream) cudaStreamSynchronize(dc.stream);
-    dc.arena.release();
-    dc.io.release();
-    if (dc.small) cudaFree(dc.small);
-    if (dc.copy_stream) cudaStreamDestroy(dc.copy_stream);
-    for (auto& e : dc.ev_copy)
-      if (e) cudaEventDestroy(e);
-    for (auto& e : dc.ev)
-      if (e) cudaEventDestroy(e);
-    if (dc.stream && dc.owns_stream) cudaStreamDestroy(dc.stream);
-  }
-  delete ctx;
+  if (!ctx || ctx->closed.exchange(1)) return MSM_ERR_INVALID;
+  // scratch goes now; streams and the context object stay while resident bases still refer to them
+  if (ctx->refs.load() > 1)
+    for (auto& dc : ctx->devs) {
+      cudaSetDevice(dc.dev);
+      if (dc.stream) cudaStreamSynchronize(dc.stream);
+      dc.arena.release();
+      dc.io.release();
+    }
+  ctx_unref(ctx);
   return MSM_OK;
 }
 
@@ -249,6 +281,7 @@ static int make_resident(msm_ctx* ctx, const void* xy, size_t n, bool sharded, b
   msm_bases* b = new msm_bases();
   b->ctx = ctx;
   b->n = n;
+  b->table_policy = default_table_policy();
   const size_t n_dev = sharded ? ctx->devs.size() : 1;
   const size_t chunk = n_dev ? (n + n_dev - 1) / n_dev : 0;
   auto fail = [&](const std::string& what) {
@@ -291,6 +324,15 @@ static int make_resident(msm_ctx* ctx, const void* xy, size_t n, bool sharded, b
       b->shards.push_back(sh);
     }
   }
+  ctx->refs.fetch_add(1);
+  if (b->table_policy == MSM_TABLE_EAGER && !sharded) {
+    // best effort: a table that does not fit leaves the plain resident copy in charge
+    for (auto& sh : b->shards)
+      if (ops->build_table(ctx, sh, 0, 0) == MSM_OK) {
+        b->table_L = sh.n;
+        b->table_chunks = 1;
+      }
+  }
   *out = b;
   return MSM_OK;
 }
@@ -311,6 +353,21 @@ static int precompute_tables(msm_ctx* ctx, msm_bases* b, uint32_t window_bits, s
     int rc = ctx->ops->build_table(ctx, sh, window_bits, chunk_len);
     if (rc != MSM_OK) return rc;
   }
+  b->table_explicit = true;
+  return MSM_OK;
+}
+int msm_bases_set_table_policy(msm_ctx* ctx, msm_bases* b, int policy) {
+  if (!ctx || !b || b->ctx != ctx || policy < MSM_TABLE_OFF || policy > MSM_TABLE_EAGER) return MSM_ERR_INVALID;
+  b->table_policy = policy;
+  if (policy == MSM_TABLE_EAGER && !msm_bases_table_window(b)) {
+    int rc = precompute_tables(ctx, b, 0, 0);
+    b->table_explicit = false;
+    if (rc == MSM_OK && !b->shards.empty()) {
+      b->table_L = b->shards[0].n;
+      b->table_chunks = 1;
+    }
+    return rc;
+  }
   return MSM_OK;
 }
 int msm_bases_precompute(msm_ctx* ctx, msm_bases* b, uint32_t window_bits) {
@@ -330,7 +387,9 @@ int msm_bases_free(msm_bases* b) {
     if (s.owned && s.ptr) cudaFree(s.ptr);
     if (s.table) cudaFree(s.table);
   }
+  msm_ctx* ctx = b->ctx;
   delete b;
+  ctx_unref(ctx);
   return MSM_OK;
 }
 

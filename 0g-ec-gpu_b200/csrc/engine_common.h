@@ -77,6 +77,10 @@ struct msm_ctx {
   std::string err;
   msm_timings tm{};
   uint32_t window_override = 0;
+  // 1 for the caller's handle + 1 per live msm_bases: msm_ctx_destroy only marks the context closed while
+  // resident bases still point at it; the last msm_bases_free (or msm_ctx_destroy) tears it down
+  std::atomic<int> refs{1};
+  std::atomic<int> closed{0};
 };
 
 struct msm_bases {
@@ -91,6 +95,13 @@ struct msm_bases {
     uint32_t table_c = 0, table_W = 0;
   };
   std::vector<Shard> shards;
+  // Window-table policy (msm_bases_set_table_policy): MSM_TABLE_OFF never, MSM_TABLE_LAZY on the second
+  // multiple_multiexp call of the same (L, num_chunks) shape, MSM_TABLE_EAGER at upload (whole-shard shape).
+  int table_policy = 1;
+  bool table_explicit = false;   // built by msm_bases_precompute[_chunked]: never rebuilt behind the caller's back
+  bool table_failed = false;     // the lazy build for the current shape did not fit: stop trying
+  size_t shape_L = 0, table_L = 0;
+  uint32_t shape_chunks = 0, shape_calls = 0, table_chunks = 0;
 };
 
 namespace msm {

@@ -11,6 +11,7 @@
 
 #include "engine_common.h"
 #include "kernels.cuh"
+#include "bucket_affine.cuh"
 #include "ecfft.cuh"
 
 namespace msm {
@@ -86,13 +87,24 @@ struct Plan {
   uint32_t bin_shift;  // binned sort: low bucket-id bits sorted inside a bin
   uint64_t E_max;
   size_t scratch_bytes;
+  // affine halving rounds before the XYZZ slice kernel (bucket_affine.cuh); 0: none
+  uint32_t ba_rounds = 0, ba_threads = 0, ba_batch = 0;
+  uint32_t S_tail = 0, n_slices_tail = 0;  // slice geometry of the XYZZ kernel over the points the rounds leave
+  uint64_t ba_cap[2] = {0, 0};             // capacity (points) of the two ping-pong point arrays
 };
+
+// G1 fields on 32-bit limbs only (the Fq2 instantiations have no registers to spare)
+template <class F> constexpr bool ba_supported() { return F::N % 4 == 0 && F::N <= 12 && F::API_WORDS == F::N; }
 
 // table_c != 0: the bases are a window table built for window size table_c covering exactly L points
 template <class F>
 int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, Plan& pl, uint32_t table_c = 0,
               uint32_t n_sub = 1, uint32_t table_stride = 0) {
   if (L == 0 || num_chunks == 0 || n_lines == 0 || num_chunks > L) return MSM_ERR_INVALID;
+  if (n_lines > 65535) {  // the line index is gridDim.y of the bucket kernels
+    set_error(ctx, "multiple_multiexp: more than 65535 base lines per call");
+    return MSM_ERR_TOO_LARGE;
+  }
   Geometry& g = pl.geo;
   g.fold = table_c ? 1 : 0;
   g.table_stride = table_stride ? table_stride : L;
@@ -181,6 +193,45 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     b += Arena::padded((size_t)3 * n_lines * 4) + Arena::padded((size_t)n_lines * pl.slices_cap * 4) +
          2 * Arena::padded(n_lines * heavy_cap * 4) + Arena::padded(n_lines * chunk_cap * 4) +
          Arena::padded(n_lines * chunk_cap * sizeof(Xyzz<F>));
+  }
+  // Affine halving rounds: worth it while a round still gives every resident thread a batch long enough to
+  // amortise its inversion (~380 products) and buckets still hold a few entries each.
+  pl.ba_rounds = 0;
+  if (ba_supported<F>() && n_lines == 1 && pl.E_max < (1ull << 30)) {
+    const uint32_t bps = F::N <= 8 ? 3 : 2;
+    pl.ba_threads = 148u * bps * BA_BLOCK;
+    pl.ba_batch = 1024;
+    if (const char* env = getenv("MSM_B200_BA_BATCH")) pl.ba_batch = (uint32_t)std::max(16, atoi(env));
+    uint32_t min_per_thread = 96;
+    if (const char* env = getenv("MSM_B200_BA_MIN_BATCH")) min_per_thread = (uint32_t)std::max(1, atoi(env));
+    int force = -1;
+    if (const char* env = getenv("MSM_B200_BA_ROUNDS")) force = atoi(env);
+    if (const char* env = getenv("MSM_B200_BA")) {
+      if (atoi(env) == 0) force = 0;
+    }
+    uint64_t eb = pl.E_max / n_sub + g.W;  // entries of one sub-batch, upper bound
+    uint32_t r = 0;
+    while (r < 8) {
+      const bool want = force >= 0 ? (int)r < force
+                                   : (eb / 2 >= (uint64_t)pl.ba_threads * min_per_thread && eb >= 3ull * g.NB);
+      if (!want) break;
+      eb = (eb + g.NB) / 2 + 1;
+      if (r < 2) pl.ba_cap[r] = eb;
+      else pl.ba_cap[r & 1] = std::max(pl.ba_cap[r & 1], eb);
+      r++;
+    }
+    pl.ba_rounds = r;
+    if (r) {
+      uint32_t St = (uint32_t)(eb / (148ull * 512 * 8));
+      St = St < 8 ? 8 : (St > 1024 ? 1024 : St);
+      if ((eb + St - 1) / St > pl.slices_cap) St = (uint32_t)((eb + pl.slices_cap - 1) / pl.slices_cap);
+      pl.S_tail = St;
+      pl.n_slices_tail = (uint32_t)((eb + St - 1) / St);
+      b += Arena::padded(pl.ba_cap[0] * sizeof(PackedAffine<F>)) + Arena::padded(pl.ba_cap[1] * sizeof(PackedAffine<F>));
+      b += 2 * Arena::padded((size_t)(g.NB + 1) * 4);                                   // offsets, ping-pong
+      b += Arena::padded((size_t)pl.ba_threads * pl.ba_batch * F::N * 4);               // prefix products
+      b += Arena::padded((size_t)pl.ba_threads * pl.ba_batch * 4);                      // input index | kind
+    }
   }
   pl.scratch_bytes = b;
   return MSM_OK;
@@ -376,16 +427,51 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     dim3 grid((n_slices + tb - 1) / tb, pl.n_lines);
     CU_TRY(ctx, cudaMemsetAsync(fl.counts, 0, (size_t)3 * pl.n_lines * 4, st));
     if (!carry_in) CU_TRY(ctx, cudaMemsetAsync(acc_sb, 0, (size_t)g.NB * pl.n_lines * sizeof(Xyzz<F>), st));  // all infinity
-    k_accumulate<F><<<grid, tb, 0, st>>>(bases_sb, line_stride, entries, bucket_start, g.NB, bucket_start + g.NB,
-                                         S, n_slices, acc_sb, partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap);
+    const uint32_t* acc_starts = bucket_start;  // bucket offsets of what the XYZZ kernel walks
+    bool ba_done = false;
+    if constexpr (ba_supported<F>()) {
+      if (pl.ba_rounds) {
+        // affine halving rounds (bucket_affine.cuh): entries -> points[0] -> points[1] -> points[0] ...
+        PackedAffine<F>* pts[2] = {dc.arena.take<PackedAffine<F>>(pl.ba_cap[0]), dc.arena.take<PackedAffine<F>>(pl.ba_cap[1])};
+        uint32_t* offs[2] = {dc.arena.take<uint32_t>(g.NB + 1), dc.arena.take<uint32_t>(g.NB + 1)};
+        uint32_t* sc_prefix = dc.arena.take<uint32_t>((size_t)pl.ba_threads * pl.ba_batch * F::N);
+        uint32_t* sc_idx = dc.arena.take<uint32_t>((size_t)pl.ba_threads * pl.ba_batch);
+        const uint32_t* off_in = bucket_start;
+        const uint32_t ba_grid = pl.ba_threads / BA_BLOCK;
+        for (uint32_t r = 0; r < pl.ba_rounds; r++) {
+          uint32_t* off_out = offs[r & 1];
+          k_halve_counts<<<(g.NB + 255) / 256, 256, 0, st>>>(off_in, g.NB, counts);
+          const SortBuffers hb{counts, off_out, cursor, tile_sums, nullptr};
+          enqueue_bucket_scan(st, g, hb);
+          if (r == 0)
+            k_affine_round<F, true><<<ba_grid, BA_BLOCK, 0, st>>>(bases_sb, entries, off_in, off_out, g.NB, pl.ba_batch,
+                                                                 pts[0], sc_prefix, sc_idx);
+          else
+            k_affine_round<F, false><<<ba_grid, BA_BLOCK, 0, st>>>(pts[(r - 1) & 1], nullptr, off_in, off_out, g.NB,
+                                                                  pl.ba_batch, pts[r & 1], sc_prefix, sc_idx);
+          off_in = off_out;
+          dc.launches += 5;
+        }
+        acc_starts = off_in;
+        S = pl.S_tail;
+        n_slices = pl.n_slices_tail;
+        grid = dim3((n_slices + tb - 1) / tb, 1);
+        k_accumulate<F><<<grid, tb, 0, st>>>(pts[(pl.ba_rounds - 1) & 1], 0u, nullptr, acc_starts, g.NB, acc_starts + g.NB, S,
+                                             n_slices, acc_sb, partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap);
+        ba_done = true;
+      }
+    }
+    if (!ba_done)
+      k_accumulate<F><<<grid, tb, 0, st>>>(bases_sb, line_stride, entries, bucket_start, g.NB, bucket_start + g.NB,
+                                           S, n_slices, acc_sb, partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap);
     // at most one cut bucket per slice
-    k_fixup_cut<F><<<grid, tb, 0, st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials, fl);
+    k_fixup_cut<F><<<grid, tb, 0, st>>>(acc_starts, g.NB, S, n_slices, acc_sb, partials, fl);
     const uint32_t hblocks = (fl.chunk_cap + 3) / 4;
     dim3 hgrid(hblocks < 148 * 8 ? hblocks : 148 * 8, pl.n_lines);
-    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, S, n_slices, acc_sb, partials, fl,
+    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(acc_starts, g.NB, S, n_slices, acc_sb, partials, fl,
                                                              chunk_out);
     dim3 fgrid2(hblocks < 148 ? hblocks : 148, pl.n_lines);
-    k_fixup_heavy_final<F><<<fgrid2, tb, tb * sizeof(Xyzz<F>), st>>>(bucket_start, g.NB, S, acc_sb, fl, chunk_out);
+    k_fixup_heavy_final<F><<<fgrid2, tb, tb * sizeof(Xyzz<F>), st>>>(acc_starts, g.NB, S, acc_sb, fl, chunk_out);
     dc.launches += 9;
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[3], st));
@@ -436,6 +522,8 @@ inline void collect_timings(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, bool ha
   t.sub_batches = pl.n_sub;
 }
 
+template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint32_t c, size_t chunk_len, bool budgeted = false);
+
 template <class F>
 int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* scalars, size_t L,
                            uint32_t num_chunks, void* out, bool device_io) {
@@ -450,12 +538,53 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   const uint32_t n_lines = (uint32_t)(bases->n / L);  // ag-cuda-ec/src/multiexp.rs:28-30
   DeviceCtx& dc = ctx->devs[0];
   CU_TRY(ctx, cudaSetDevice(dc.dev));
+  // Lazy window table (include/msm_b200.h, "Window tables by policy"): the second call of one shape
+  // builds the table that shape wants, if the cost model wants one and it fits the memory budget.
+  {
+    msm_bases* mb = const_cast<msm_bases*>(bases);
+    if (mb->shape_L == L && mb->shape_chunks == num_chunks) {
+      mb->shape_calls++;
+    } else {
+      mb->shape_L = L;
+      mb->shape_chunks = num_chunks;
+      mb->shape_calls = 1;
+      mb->table_failed = false;
+    }
+    msm_bases::Shard& shm = mb->shards[0];
+    const bool fits_shape = shm.table && mb->table_L == L && mb->table_chunks == num_chunks;
+    if (mb->table_policy != MSM_TABLE_OFF && !mb->table_explicit && !fits_shape && !mb->table_failed &&
+        mb->shape_calls >= 2 && !ctx->window_override && !getenv("MSM_B200_WINDOW") && num_chunks >= 1 && num_chunks <= L) {
+      const bool whole = num_chunks == 1 && n_lines == 1 && L == shm.n;
+      const uint32_t chunk_len = (uint32_t)(L / num_chunks);
+      const uint32_t bits = scalar_bits(ctx->curve);
+      bool want = whole;
+      if (!whole && (size_t)L * n_lines == shm.n) {
+        const uint64_t groups = (uint64_t)num_chunks * n_lines;
+        const uint32_t tc = choose_table_window(chunk_len, bits, groups, shm.n);
+        double plain_cost = 0;
+        choose_window(chunk_len, bits, groups, sizeof(Xyzz<F>), &plain_cost);
+        want = tc != 0 && fold_cost(tc, chunk_len, bits, groups) < plain_cost;
+      }
+      if (want) {
+        int trc = build_table_impl<F>(ctx, shm, 0, whole ? 0 : chunk_len, /*budgeted=*/true);
+        if (trc == MSM_OK) {
+          mb->table_L = L;
+          mb->table_chunks = num_chunks;
+        } else {
+          mb->table_failed = true;  // over budget or out of memory: the plain resident copy keeps serving
+          cudaGetLastError();
+        }
+      } else {
+        mb->table_failed = true;
+      }
+    }
+  }
   const msm_bases::Shard& sh0 = bases->shards[0];
   // A window table serves (i) the call it was built for -- one MSM over the whole shard -- and (ii) any
   // chunked / multi-line call for which folding all windows of a task into one bucket set is cheaper
   // than the plain per-window bucket sets at the window size the plain path would pick.
   bool use_table = false;
-  if (sh0.table && !ctx->window_override && num_chunks >= 1 && num_chunks <= L) {
+  if (sh0.table && !ctx->window_override && !getenv("MSM_B200_WINDOW") && num_chunks >= 1 && num_chunks <= L) {
     if (num_chunks == 1 && n_lines == 1 && L == sh0.n) {
       use_table = true;
     } else if (!getenv("MSM_B200_NO_CHUNK_TABLE")) {
@@ -472,7 +601,7 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   // previous chunk is already being sorted and accumulated (the 32 B/scalar upload is ~20 % of the
   // call otherwise).
   uint32_t n_sub = 1;
-  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 22)) n_sub = L >= (1u << 23) ? 8 : 4;
+  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 20)) n_sub = L >= (1u << 23) ? 8 : 4;
   if (const char* env = getenv("MSM_B200_PIPELINE")) {
     const int v = atoi(env);
     // MSM_B200_PIPELINE_DEVICE: also split device-resident rows (measurement of the split's own cost)
@@ -487,6 +616,16 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   const uint32_t* d_scalars;
   ApiJacobian<F>* d_out;
   const size_t out_bytes = (size_t)pl.n_tasks * sizeof(ApiJacobian<F>);
+  // Once the pipelined sub-batch copies are queued they read the caller's buffer asynchronously (truly so
+  // for pinned memory): every exit before the final synchronise -- error or abort -- drains both streams
+  // first, so the caller may free / unregister the buffer as soon as the call returns.
+  struct Drain {
+    cudaStream_t a = nullptr, b = nullptr;
+    ~Drain() {
+      if (a) cudaStreamSynchronize(a);
+      if (b) cudaStreamSynchronize(b);
+    }
+  } drain;
   if (device_io) {
     d_scalars = static_cast<const uint32_t*>(scalars);
     d_out = static_cast<ApiJacobian<F>*>(out);
@@ -498,6 +637,8 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
     if (pl.n_sub > 1) {
       // the copy stream must not overwrite the staging area while an earlier call still reads it
       CU_TRY(ctx, cudaStreamWaitEvent(dc.copy_stream, dc.ev[0], 0));
+      drain.a = dc.copy_stream;
+      drain.b = dc.stream;
       const size_t L_sub = (pl.geo.L + pl.n_sub - 1) / pl.n_sub;
       for (uint32_t sb = 0; sb < pl.n_sub; sb++) {
         const size_t first = std::min((size_t)sb * L_sub, (size_t)L);
@@ -520,6 +661,7 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   }
   if (!device_io) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, dc.stream));
   CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
+  drain.a = drain.b = nullptr;  // every sub-batch copy was waited for by the kernels that just finished
   collect_timings(ctx, dc, pl, !device_io);
   return MSM_OK;
 }
@@ -684,7 +826,7 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
 }
 
 // Window table for one resident shard (msm_bases_precompute).
-template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint32_t c, size_t chunk_len) {
+template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint32_t c, size_t chunk_len, bool budgeted) {
   if (sh.n == 0) return MSM_OK;
   DeviceCtx& dc = ctx->devs[sh.dev_idx];
   CU_TRY(ctx, cudaSetDevice(dc.dev));
@@ -718,8 +860,21 @@ template <class F> int build_table_impl(msm_ctx* ctx, msm_bases::Shard& sh, uint
   if (sh.table) {
     cudaFree(sh.table);
     sh.table = nullptr;
+    sh.table_c = sh.table_W = 0;
   }
-  CU_TRY(ctx, cudaMalloc(&sh.table, (size_t)W * sh.n * sizeof(PackedAffine<F>)));
+  const size_t table_bytes = (size_t)W * sh.n * sizeof(PackedAffine<F>);
+  if (budgeted) {
+    // tables built by policy (nobody asked for them) stay within a stated budget
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    double budget = 0.5 * (double)total_b;
+    if (const char* env = getenv("MSM_B200_TABLE_BUDGET_GB")) budget = atof(env) * 1e9;
+    if ((double)table_bytes > budget || (double)table_bytes > 0.8 * (double)free_b) {
+      set_error(ctx, "window table over budget");
+      return MSM_ERR_TOO_LARGE;
+    }
+  }
+  CU_TRY(ctx, cudaMalloc(&sh.table, table_bytes));
   k_build_tables<F><<<(uint32_t)((sh.n + 63) / 64), 64, 0, dc.stream>>>(
       static_cast<const PackedAffine<F>*>(sh.ptr), (uint32_t)sh.n, c, W, static_cast<PackedAffine<F>*>(sh.table));
   dc.launches += 1;
@@ -935,7 +1090,7 @@ template <class F> FieldOps make_field_ops(const char* name) {
   o.multiple_multiexp = &multiple_multiexp_impl<F>;
   o.multiexp = &multiexp_impl<F>;
   o.convert_bases = &convert_bases_impl<F>;
-  o.build_table = &build_table_impl<F>;
+  o.build_table = [](msm_ctx* c, msm_bases::Shard& sh, uint32_t w, size_t cl) { return build_table_impl<F>(c, sh, w, cl, false); };
   o.synth_points = &synth_points_impl<F>;
   o.test_fq = &test_fq_impl<F>;
   o.test_ec = &test_ec_impl<F>;

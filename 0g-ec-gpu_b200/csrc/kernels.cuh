@@ -697,10 +697,13 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
   // entry pos starts, and the entry index one further ahead: the two dependent loads of the gather
   // are off the critical path of the IMAD chains.
   constexpr int WORDS = 2 * F::PACKED_WORDS;
+  // entries == nullptr: the points to add are bases[s .. e) themselves, already signed (the output of the
+  // affine halving rounds, bucket_affine.cuh)
+  const bool direct = entries == nullptr;
   uint32_t nxt[WORDS];
-  uint32_t ent = __ldg(entries + s);
+  uint32_t ent = direct ? s : __ldg(entries + s);
   load_base_words<F>(bases + (ent & 0x7fffffffu), nxt);
-  uint32_t ent_ahead = s + 1 < e ? __ldg(entries + s + 1) : ent;
+  uint32_t ent_ahead = s + 1 < e ? (direct ? s + 1 : __ldg(entries + s + 1)) : ent;
   for (uint32_t pos = s; pos < e; pos++) {
     if (pos == gend) {
       // bucket g is complete: flush and move to the next non-empty bucket
@@ -718,7 +721,7 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
     ent = ent_ahead;
     if (pos + 1 < e) {
       load_base_words<F>(bases + (ent & 0x7fffffffu), nxt);
-      if (pos + 2 < e) ent_ahead = __ldg(entries + pos + 2);
+      if (pos + 2 < e) ent_ahead = direct ? pos + 2 : __ldg(entries + pos + 2);
     }
     if (finite) {
       pt = aff_cneg<F>(pt, negate);

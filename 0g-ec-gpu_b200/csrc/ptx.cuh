@@ -21,6 +21,15 @@
 #define MSM_HD inline
 #define MSM_D inline
 #define MSM_COLD inline
+#ifndef __restrict__
+#define __restrict__ __restrict
+#endif
+// host build (test vehicle): the few CUDA built-ins the per-thread device functions use
+struct alignas(16) uint4 {
+  uint32_t x, y, z, w;
+};
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+template <class T> inline T __ldg(const T* p) { return *p; }
 #endif
 
 namespace msm {

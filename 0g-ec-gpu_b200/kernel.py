@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 from ._lib import BN254_G1, EcErrorAborted, check, fq_bytes, load_library
-from .multiexp import Workspace, _as_u8
+from .multiexp import DeviceData, Workspace, _as_u8
 
 
 class Worker:
@@ -90,7 +90,7 @@ class MultiexpKernel:
         h = ctypes.c_void_p()
         check(load_library().msm_bases_upload_sharded(self._ws.handle, b.ctypes.data, b.size // pt, ctypes.byref(h)),
               self._ws.handle)
-        return h
+        return DeviceData(self._ws, h)  # freed on drop, like every other resident handle
 
     def multiexp_resident(self, resident, exps, skip: int = 0) -> np.ndarray:
         e = _as_u8(exps, 32, "exps")

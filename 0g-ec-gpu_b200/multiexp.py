@@ -67,6 +67,18 @@ class DeviceData:
         self.workspace = workspace
         self._h = handle
 
+    @property
+    def _as_parameter_(self):  # lets ctypes take a DeviceData wherever the C ABI wants an msm_bases*
+        return self._h
+
+    def set_table_policy(self, policy: int):
+        """Engine extension (msm_bases_set_table_policy): 0 off, 1 lazy (default), 2 eager."""
+        check(load_library().msm_bases_set_table_policy(self.workspace.handle, self._h, policy), self.workspace.handle,
+              cuda_style=True)
+
+    def table_window(self) -> int:
+        return load_library().msm_bases_table_window(self._h)
+
     def size(self) -> int:
         return load_library().msm_bases_size_bytes(self._h)
 

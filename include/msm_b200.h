@@ -100,8 +100,23 @@ const char* msm_field_impl(const msm_ctx* ctx);
 int msm_set_stream(msm_ctx* ctx, void* cuda_stream);
 
 /* ---- resident bases -------------------------------------------------------------------- */
-/* upload_multiexp_bases (ag-cuda-ec/src/multiexp.rs:12-19): copy n_points {x,y} Montgomery
- * points from host memory to device 0 of the context and keep them resident. */
+/* Lifetime: an msm_bases keeps its context alive.  msm_ctx_destroy on a context that still has live
+ * msm_bases only closes it (every later call on it returns MSM_ERR_INVALID); the device resources go
+ * when the last msm_bases_free has run.  So Drop order in the Rust shim (a thread-local workspace
+ * dying before a DeviceData that was sent to another thread) is harmless.
+ *
+ * upload_multiexp_bases (ag-cuda-ec/src/multiexp.rs:12-19): copy n_points {x,y} Montgomery
+ * points from host memory to device 0 of the context and keep them resident.
+ *
+ * Window tables by policy: the reference API has no "precompute" step, so the engine decides by itself.
+ * Default MSM_TABLE_LAZY: the second msm_multiple_multiexp[_device] call with the same (L, num_chunks)
+ * shape on the same msm_bases builds the window table described at msm_bases_precompute below (once;
+ * 0.2 - 0.9 s for 2^24 points), provided it fits the budget: table bytes <= MSM_B200_TABLE_BUDGET_GB
+ * (default: half of the device's memory) and <= 80 % of the memory free at that moment; every later
+ * call of that shape uses it.  A one-off call therefore never pays for a table, a prover that reuses
+ * its SRS gets the fast path without calling anything outside the reference's API.  A different
+ * shape seen twice in a row replaces the table.  Environment MSM_B200_TABLE=off|lazy|eager sets the
+ * default policy of new msm_bases. */
 int msm_bases_upload(msm_ctx* ctx, const void* xy_mont, size_t n_points, msm_bases** out);
 /* Same, but split contiguously over all devices of the context, ceil(n/devices) points each:
  * the partition MultiexpKernel::parallel_multiexp uses (ec-gpu-proxy/src/multiexp.rs:329-337). */
@@ -124,6 +139,10 @@ int msm_bases_precompute(msm_ctx* ctx, msm_bases* b, uint32_t window_bits);
 int msm_bases_precompute_chunked(msm_ctx* ctx, msm_bases* b, size_t chunk_len);
 /* Window size of the table (0: none). */
 uint32_t msm_bases_table_window(const msm_bases* b);
+/* Policy for this handle (overrides MSM_B200_TABLE): MSM_TABLE_OFF drops nothing but never builds;
+ * MSM_TABLE_LAZY as described above; MSM_TABLE_EAGER builds the whole-shard table now. */
+typedef enum { MSM_TABLE_OFF = 0, MSM_TABLE_LAZY = 1, MSM_TABLE_EAGER = 2 } msm_table_policy;
+int msm_bases_set_table_policy(msm_ctx* ctx, msm_bases* b, int policy);
 /* DeviceData::size (ag-cuda-proxy/src/params.rs:209): bytes. */
 size_t msm_bases_size_bytes(const msm_bases* b);
 size_t msm_bases_num_points(const msm_bases* b);

@@ -50,6 +50,8 @@ extern "C" {
     pub fn msm_bases_upload_sharded(ctx: *mut msm_ctx, xy_mont: *const c_void, n_points: usize, out: *mut *mut msm_bases) -> c_int;
     pub fn msm_bases_precompute(ctx: *mut msm_ctx, b: *mut msm_bases, window_bits: u32) -> c_int;
     pub fn msm_bases_precompute_chunked(ctx: *mut msm_ctx, b: *mut msm_bases, chunk_len: usize) -> c_int;
+    /// 0 = off, 1 = lazy (default: the 2nd call of a shape builds the window table), 2 = eager.
+    pub fn msm_bases_set_table_policy(ctx: *mut msm_ctx, b: *mut msm_bases, policy: c_int) -> c_int;
     pub fn msm_bases_size_bytes(b: *const msm_bases) -> usize;
     pub fn msm_bases_free(b: *mut msm_bases) -> c_int;
     pub fn msm_multiple_multiexp(

@@ -3,7 +3,9 @@
 // lazy-reduction bound assertions switched on (-DMSM_CHECK_BOUNDS).  Test vehicle only.
 #include <cstddef>
 #include <cstring>
+#include <vector>
 #include "../../0g-ec-gpu_b200/csrc/ec.cuh"
+#include "../../0g-ec-gpu_b200/csrc/bucket_affine.cuh"
 using namespace msm;
 
 template <class F> static int fq_op(int op, const uint32_t* a, const uint32_t* b, const uint32_t* r2, uint32_t* o, size_t n) {
@@ -112,4 +114,55 @@ extern "C" int host_madd_chain(int curve, int impl, const void* pts, size_t m, s
 #define CALL(F) madd_chain<F>((const uint32_t*)pts, m, steps, lanes, (uint32_t*)o)
   DISPATCH(CALL)
 #undef CALL
+}
+
+// Affine halving rounds (csrc/bucket_affine.cuh), the per-thread device function run thread by thread:
+// `rounds` rounds over the sorted entry list, T emulated threads, batches of at most m_max items.
+// bases: API-layout affine points; entries: index | sign << 31, grouped by bucket (off0[NB + 1]).
+// Returns the number of points left; out_pts (API affine layout) / out_off ([NB + 1]) describe them.
+template <class F>
+static long ba_rounds(const uint32_t* bases_api, size_t n_bases, const uint32_t* entries, const uint32_t* off0, uint32_t NB,
+                      uint32_t rounds, uint32_t T, uint32_t m_max, uint32_t* out_pts, uint32_t* out_off) {
+  std::vector<PackedAffine<F>> packed(n_bases);
+  for (size_t i = 0; i < n_bases; i++) {
+    const ApiAffine<F>* a = reinterpret_cast<const ApiAffine<F>*>(bases_api) + i;
+    F::api_to_packed(a->x, packed[i].x);
+    F::api_to_packed(a->y, packed[i].y);
+  }
+  std::vector<uint32_t> off_in(off0, off0 + NB + 1), off_out(NB + 1);
+  std::vector<PackedAffine<F>> cur, nxt;
+  std::vector<uint32_t> sc_prefix((size_t)T * m_max * F::N), sc_idx((size_t)T * m_max);
+  for (uint32_t r = 0; r < rounds; r++) {
+    off_out[0] = 0;
+    for (uint32_t g = 0; g < NB; g++) off_out[g + 1] = off_out[g] + ((off_in[g + 1] - off_in[g] + 1) >> 1);
+    nxt.assign(off_out[NB] + 1, PackedAffine<F>{});
+    for (uint32_t t = 0; t < T; t++) {
+      if (r == 0)
+        ba_round_thread<F, true>(t, T, packed.data(), entries, off_in.data(), off_out.data(), NB, m_max, nxt.data(),
+                                 sc_prefix.data(), sc_idx.data());
+      else
+        ba_round_thread<F, false>(t, T, cur.data(), nullptr, off_in.data(), off_out.data(), NB, m_max, nxt.data(),
+                                  sc_prefix.data(), sc_idx.data());
+    }
+    cur.swap(nxt);
+    off_in = off_out;
+  }
+  const uint32_t left = off_in[NB];
+  for (uint32_t i = 0; i < left; i++) {
+    ApiAffine<F>* o = reinterpret_cast<ApiAffine<F>*>(out_pts) + i;
+    F::to_api(F::unpack(cur[i].x), o->x);
+    F::to_api(F::unpack(cur[i].y), o->y);
+  }
+  for (uint32_t g = 0; g <= NB; g++) out_off[g] = off_in[g];
+  return (long)left;
+}
+extern "C" long host_ba_rounds(int curve, const void* bases, size_t n_bases, const void* entries, const void* off0,
+                               uint32_t NB, uint32_t rounds, uint32_t T, uint32_t m_max, void* out_pts, void* out_off) {
+  if (curve == 0)
+    return ba_rounds<FieldSatLazy<Bn254Fq>>((const uint32_t*)bases, n_bases, (const uint32_t*)entries, (const uint32_t*)off0,
+                                            NB, rounds, T, m_max, (uint32_t*)out_pts, (uint32_t*)out_off);
+  if (curve == 1)
+    return ba_rounds<FieldSatLazy<Bls381Fq>>((const uint32_t*)bases, n_bases, (const uint32_t*)entries, (const uint32_t*)off0,
+                                             NB, rounds, T, m_max, (uint32_t*)out_pts, (uint32_t*)out_off);
+  return -100;
 }

@@ -280,7 +280,7 @@ def test_window_table_sharded_resident(engine, oracle):
     assert_same_points(oracle, 0, got, oracle.multiexp_cpu(0, pts, sc), "resident + table")
     part = kern.multiexp_resident(res, sc[:1000], 5)  # a sub-range falls back to the plain copy
     assert_same_points(oracle, 0, part, oracle.multiexp_cpu(0, pts[5:], sc[:1000]), "sub-range")
-    lib.msm_bases_free(res)
+    res.free()
 
 
 @pytest.mark.parametrize("curve", CURVES)
@@ -437,6 +437,99 @@ def test_context_busy_and_errors(engine, oracle):
         kern2.multiexp(engine.Worker(), pts, oracle.gen_scalars(0, 1, 64), 0)
 
 
+def test_context_busy_under_a_real_race(engine, oracle):
+    """Two host threads on ONE workspace: while thread A is inside a long multiple_multiexp call, thread
+    B's call on the same context must come back with CudaError::ContextAlreadyInUse (MSM_ERR_BUSY,
+    ag-cuda-proxy/src/context.rs:20-27) -- and A's result must be unharmed."""
+    import threading
+
+    curve, n = 0, 1 << 20
+    w = engine.Workspace(curve)
+    pts, sc = _synth(engine, w, curve, n)
+    bases = engine.upload_multiexp_bases(w, pts)
+    bases.set_table_policy(0)
+    small = oracle.gen_scalars(curve, 3, n)
+    inside = threading.Event()
+    results, busy, other = [], [], []
+
+    def long_call():
+        inside.set()
+        for _ in range(6):
+            results.append(engine.multiple_multiexp(w, bases, sc, 1, 8, True))
+
+    a = threading.Thread(target=long_call)
+    a.start()
+    inside.wait()
+    while a.is_alive():
+        try:
+            engine.multiple_multiexp(w, bases, small, 1, 8, True)
+        except engine.CudaError as e:
+            (busy if e.name == "ContextAlreadyInUse" else other).append(e)
+    a.join()
+    assert not other, other
+    assert busy, "the second thread never collided with the call in flight"
+    want = oracle.multiexp_cpu(curve, pts, sc)
+    for r in results:
+        assert_same_points(oracle, curve, r, want, "result of the call that held the context")
+    bases.free()
+    w.close()
+
+
+def test_abort_mid_call_with_registered_scalars(engine, oracle):
+    """Abort flag raised while a pipelined call (pinned host scalars, sub-batch copies on the copy stream) is
+    in flight: the call returns OK or Aborted, and in both cases no copy may still be reading the caller's
+    buffer -- it is unregistered and overwritten right away, and the next call on the context is correct."""
+    import threading
+    import time
+
+    curve, n = 0, 1 << 22
+    lib = engine.load_library()
+    w = engine.Workspace(curve)
+    pts, sc = _synth(engine, w, curve, n)
+    bases = engine.upload_multiexp_bases(w, pts)
+    bases.set_table_policy(0)
+    want = oracle.multiexp_cpu(curve, pts, sc)
+    flag = ctypes.c_int(0)
+    lib.msm_set_abort_flag(w.handle, ctypes.addressof(flag))
+    outcomes = set()
+    for delay in (0.0, 0.0005, 0.002, 0.005):
+        buf = sc.copy()
+        assert lib.msm_host_register(buf.ctypes.data, buf.nbytes) == 0
+        flag.value = 0
+        t = threading.Timer(delay, lambda: setattr(flag, "value", 1))
+        t.start()
+        try:
+            got = engine.multiple_multiexp(w, bases, buf, 1, 8, True)
+            assert w.timings()["sub_batches"] > 1
+            assert_same_points(oracle, curve, got, want, "call that finished before the abort")
+            outcomes.add("ok")
+        except engine.CudaError as e:  # ag_cuda_ec has no abort; the C ABI reports MSM_ERR_ABORTED as UnknownError
+            outcomes.add("aborted")
+            assert "abort" in str(e).lower() or e.name == "UnknownError"
+        t.join()
+        assert lib.msm_host_unregister(buf.ctypes.data) == 0
+        buf[:] = 0xFF  # a copy still in flight would now upload garbage
+        time.sleep(0.01)
+        flag.value = 0
+        again = engine.multiple_multiexp(w, bases, sc, 1, 8, True)
+        assert_same_points(oracle, curve, again, want, "call after an aborted one")
+    lib.msm_set_abort_flag(w.handle, None)
+    bases.free()
+    w.close()
+
+
+def test_bases_outlive_their_workspace(engine, oracle):
+    """Drop order: a DeviceData may be freed after its workspace was closed (msm_b200.h, "Lifetime")."""
+    lib = engine.load_library()
+    w = engine.Workspace(0)
+    bases = engine.upload_multiexp_bases(w, oracle.gen_points(0, 5, 256))
+    h = w.handle
+    w.close()
+    assert lib.msm_multiple_multiexp(h, bases._h, None, 0, 1, 8, 1, None) != 0  # closed context: rejected
+    assert bases.size() == 256 * 64
+    bases.free()
+
+
 def test_multi_device_split_and_gather(engine, oracle):
     """MultiexpKernel over every visible GPU: contiguous split ceil(n/devices)
     (ec-gpu-proxy/src/multiexp.rs:329-337), partial points gathered on device 0 over peer copies
@@ -456,7 +549,7 @@ def test_multi_device_split_and_gather(engine, oracle):
         assert_same_points(oracle, curve, kern.multiexp_resident(res, sc, 0), want, "resident shards")
         assert lib.msm_bases_precompute(kern.workspace.handle, res, 0) == 0
         assert_same_points(oracle, curve, kern.multiexp_resident(res, sc, 0), want, "resident shards + tables")
-        lib.msm_bases_free(res)
+        res.free()
 
 
 def test_concurrent_local_workspaces(engine, oracle):

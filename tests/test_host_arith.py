@@ -32,6 +32,9 @@ def host():
     h.host_fq_op.argtypes = [i32, i32, i32, vp, vp, vp, vp, sz]
     h.host_ec_op.argtypes = [i32, i32, i32, vp, vp, vp, sz]
     h.host_madd_chain.argtypes = [i32, i32, vp, sz, sz, sz, vp]
+    u32 = ctypes.c_uint32
+    h.host_ba_rounds.argtypes = [i32, vp, sz, vp, vp, u32, u32, u32, u32, vp, vp]
+    h.host_ba_rounds.restype = ctypes.c_long
     return h
 
 
@@ -132,3 +135,53 @@ def test_long_madd_chains_keep_invariants(host, oracle, curve, impl):
             acc = oracle.ec_op(curve, 1, acc, src[idx: idx + 1].copy())
         want[i] = acc[0]
     assert_same_points(oracle, curve, out, want, "madd chain")
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("rounds,T,m_max", [(1, 7, 5), (3, 16, 64), (5, 3, 9), (9, 1, 1000)])
+def test_affine_halving_rounds(host, oracle, curve, rounds, T, m_max):
+    """csrc/bucket_affine.cuh, the device function of one thread run thread by thread on the host: after any
+    number of halving rounds the points left in a bucket still sum to the bucket's signed entries.  Buckets:
+    empty, single, odd and even sizes, one heavy bucket spanning many threads and batches, repeated points
+    (P + P: tangent), P and -P neighbours (cancel), identity bases (0,0), an all-identity bucket."""
+    fq = FQ[curve]
+    rng = np.random.default_rng(1000 * curve + rounds)
+    m = 61
+    pts = oracle.gen_points(curve, 31, m)
+    pts[7] = 0
+    pts[8] = 0
+    neg = pts.copy()
+    neg[:, fq:] = oracle.fq_op(curve, 8, pts[:, fq:].copy())
+    NEG = 1 << 31
+    buckets = [[], [3], [4, 4], [5, 5 | NEG], [7, 9], [9, 7], [7, 8], [7], [10, 10, 10, 10], [11, 11 | NEG, 12],
+               [13, 14, 13 | NEG, 14 | NEG, 15], [], [int(x) for x in rng.integers(0, m, 301)],
+               [int(x) | (NEG if s else 0) for x, s in zip(rng.integers(0, m, 40), rng.integers(0, 2, 40))]]
+    for _ in range(30):
+        k = int(rng.integers(0, 12))
+        buckets.append([int(x) | (NEG if s else 0) for x, s in zip(rng.integers(0, m, k), rng.integers(0, 2, k))])
+    NB = len(buckets)
+    off0 = np.zeros(NB + 1, dtype=np.uint32)
+    off0[1:] = np.cumsum([len(b) for b in buckets])
+    entries = np.array([e for b in buckets for e in b], dtype=np.uint32)
+    out_pts = np.zeros((len(entries) + 1, 2 * fq), dtype=np.uint8)
+    out_off = np.zeros(NB + 1, dtype=np.uint32)
+    left = host.host_ba_rounds(curve, pts.ctypes.data, m, entries.ctypes.data, off0.ctypes.data, NB, rounds, T, m_max,
+                               out_pts.ctypes.data, out_off.ctypes.data)
+    assert left >= 0
+    n = off0[1:] - off0[:-1]
+    for _ in range(rounds):
+        n = (n + 1) // 2
+    assert (out_off[1:] - out_off[:-1] == n).all() and left == int(n.sum())
+    one = oracle.constant(curve, 1)
+
+    def total(rows):
+        acc = np.zeros((1, 3 * fq), dtype=np.uint8)
+        for r in rows:
+            if not r.any():
+                continue
+            acc = oracle.ec_op(curve, 1, acc, r.reshape(1, -1).copy())
+        return acc
+
+    got = np.concatenate([total(out_pts[out_off[g]: out_off[g + 1]]) for g in range(NB)])
+    want = np.concatenate([total([(neg if e & NEG else pts)[e & 0x7FFFFFFF] for e in b]) for b in buckets])
+    assert_same_points(oracle, curve, got, want, "bucket sums after the halving rounds")

@@ -9,7 +9,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../0g-ec-gpu_b200/csrc/ec.cuh"
-#include "../0g-ec-gpu_b200/csrc/f52.cuh"
+#include "f52.cuh"
 using namespace msm;
 
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("{\"error\": \"%s at %s\"}\n", cudaGetErrorString(e), #x); return 1; } } while (0)

@@ -16,7 +16,7 @@
 // Replaces nothing in the reference (its field layer is 32/64-bit integer only,
 // ag-build/cl/field.cl:85-299); it is the second arithmetic pipe of the accumulate kernel.
 #pragma once
-#include "ptx.cuh"
+#include "../0g-ec-gpu_b200/csrc/ptx.cuh"
 
 namespace msm {
 

@@ -8,7 +8,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../0g-ec-gpu_b200/csrc/ec.cuh"
-#include "../0g-ec-gpu_b200/csrc/f52.cuh"
+#include "f52.cuh"
 using namespace msm;
 
 template <class P, int MODE>
