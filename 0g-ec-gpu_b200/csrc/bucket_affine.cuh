@@ -12,20 +12,27 @@
 // an odd last entry is passed through), halving every bucket.  Outputs are dense: the output array of a
 // round is laid out bucket by bucket (offsets = exclusive scan of ceil(n/2), one small scan per round), so
 // a bucket of any size -- the short top window of a folded table, equal scalars -- is simply many
-// consecutive work items and needs no special handling.  After a few rounds the per-thread batches get
-// too short to amortise the inversion; the remaining points (a handful per bucket) go through the
-// existing XYZZ slice kernel, which also covers carry-in from earlier sub-batches.
+// consecutive work items and needs no special handling.  After a few rounds the batches get too short to
+// amortise the inversion; the remaining points (a handful per bucket) go through the existing XYZZ slice
+// kernel, which also covers carry-in from earlier sub-batches.
 //
-// One thread owns a contiguous range of output items and runs, per batch of at most M_max items:
-//   forward   for every item: denominator d_i (x2 - x1, or 2 y1 for equal points), running product
-//             prefix_i = d_0 ... d_(i-1) stored to a scratch column (coalesced: [item][thread]);
-//   invert    one field inversion of the batch's total product;
+// Work mapping (v2; the first version gave every thread a contiguous range and measured 165 - 200 ps per
+// addition against 150 for XYZZ: 10 scattered 32-byte sectors per addition ran into the DRAM's random-access
+// rate, not its bandwidth): a WARP owns a contiguous span of outputs and lane l takes outputs l, l + 32, ...
+// of it, so that every load and store of the round -- the two inputs of an output are neighbours -- is a
+// contiguous run across the warp.  Points between rounds are stored as two planes (all x, then all y): the
+// forward pass needs x only.  Per batch of at most M_max outputs per thread:
+//   forward   denominator d_i (x2 - x1, or 2 y1 for equal points), running product prefix_i = d_0 ... d_(i-1)
+//             stored to scratch ([item][thread]: coalesced);
+//   invert    ONE inversion per thread block: the threads' batch products are multiplied up a binary tree in
+//             shared memory, one thread inverts the root (the other blocks of the SM keep the multiplier pipe
+//             busy meanwhile), and the inverses are walked back down (2 products per level);
 //   backward  for every item in reverse: 1/d_i = inv * prefix_i, inv *= d_i, then the affine formulas.
 // Exceptional inputs are classified in the forward pass (kind stored next to the input index):
 // identity operands (0,0), P + P (tangent slope, denominator 2y), P + (-P) (result identity).
 //
 // Replaces, for large calls, the per-thread serial bucket scan of POINT_multiexp_chunk
-// (ag-build/cl/multiexp.cl:62-134) together with k_accumulate's XYZZ additions.
+// (ag-build/cl/multiexp.cl:62-134) together with most of k_accumulate's XYZZ additions.
 #pragma once
 #include "ec.cuh"
 
@@ -45,6 +52,15 @@ MSM_D uint32_t ba_find_bucket(const uint32_t* __restrict__ off, uint32_t NB, uin
 constexpr int BA_BLOCK = 128;
 constexpr uint32_t BA_KIND_COPY = 0, BA_KIND_ADD = 1, BA_KIND_DBL = 2, BA_KIND_SPECIAL = 3;
 
+// Input / output of a round.  Round 0 gathers: item a is the sorted entry entries[a] = table index | sign << 31.
+// Later rounds read the planes of the previous round: x of item a at x + a * N words, y at y + a * N.
+template <class F> struct BaPoints {
+  const PackedAffine<F>* table;  // gather source (round 0), else nullptr
+  const uint32_t* entries;
+  uint32_t* x;                   // planes (input of rounds >= 1, output of every round)
+  uint32_t* y;
+};
+
 template <class F> MSM_D void ba_store_elem(uint32_t* dst, const typename F::Elem& e) {
   static_assert(F::N % 4 == 0, "limb count must be a multiple of 4");
   uint4* q = reinterpret_cast<uint4*>(dst);
@@ -61,182 +77,215 @@ template <class F> MSM_D typename F::Elem ba_load_elem(const uint32_t* src) {
   }
   return e;
 }
-
-// Input item `a` of a round: GATHER = true reads the sorted entry (table index | sign) and fetches the base
-// point with the sign applied; otherwise the point is element `a` of the previous round's output.
-template <class F, bool GATHER>
-MSM_D const PackedAffine<F>* ba_src(const PackedAffine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
-                                    uint32_t a, bool& negate) {
+template <class F> MSM_D typename F::Elem ba_load_elem_ro(const uint32_t* src) {  // read-only path
+  typename F::Elem e;
+  const uint4* q = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int j = 0; j < F::N / 4; j++) {
+    const uint4 t = __ldg(q + j);
+    e.v[4 * j] = t.x; e.v[4 * j + 1] = t.y; e.v[4 * j + 2] = t.z; e.v[4 * j + 3] = t.w;
+  }
+  return e;
+}
+// x / y of input item a (y with the entry's sign applied when gathering)
+template <class F, bool GATHER> MSM_D typename F::Elem ba_in_x(const BaPoints<F>& in, uint32_t a) {
+  if (GATHER) return ba_load_elem_ro<F>(in.table[__ldg(in.entries + a) & 0x7fffffffu].x);
+  return ba_load_elem_ro<F>(in.x + (size_t)a * F::N);
+}
+template <class F, bool GATHER> MSM_D typename F::Elem ba_in_y(const BaPoints<F>& in, uint32_t a) {
   if (GATHER) {
-    const uint32_t ent = __ldg(entries + a);
-    negate = (ent >> 31) != 0;
-    return src + (ent & 0x7fffffffu);
+    const uint32_t ent = __ldg(in.entries + a);
+    typename F::Elem y = ba_load_elem_ro<F>(in.table[ent & 0x7fffffffu].y);
+    if (ent >> 31) y = F::template neg<2, 1>(y);  // (0,0) stays (0,0): neg maps 0 to 0
+    return y;
   }
-  negate = false;
-  return src + a;
-}
-template <class F> MSM_D typename F::Elem ba_load_x(const PackedAffine<F>* p) {
-  uint32_t w[F::PACKED_WORDS];
-  const uint4* q = reinterpret_cast<const uint4*>(p->x);
-#pragma unroll
-  for (int j = 0; j < F::PACKED_WORDS / 4; j++) {
-    const uint4 t = __ldg(q + j);
-    w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
-  }
-  return F::unpack(w);
-}
-template <class F> MSM_D typename F::Elem ba_load_y(const PackedAffine<F>* p, bool negate) {
-  uint32_t w[F::PACKED_WORDS];
-  const uint4* q = reinterpret_cast<const uint4*>(p->y);
-#pragma unroll
-  for (int j = 0; j < F::PACKED_WORDS / 4; j++) {
-    const uint4 t = __ldg(q + j);
-    w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
-  }
-  typename F::Elem y = F::unpack(w);
-  if (negate) y = F::template neg<2, 1>(y);  // (0,0) stays (0,0): neg maps 0 to 0
-  return y;
+  return ba_load_elem_ro<F>(in.y + (size_t)a * F::N);
 }
 template <class F> MSM_D bool ba_is_zero(const typename F::Elem& e) { return F::template is_multiple_of_p<0, 2>(e); }
-
-template <class F> MSM_D void ba_store_point(PackedAffine<F>* dst, const typename F::Elem& x, const typename F::Elem& y) {
-  PackedAffine<F> o;
-  F::to_packed(x, o.x);
-  F::to_packed(y, o.y);
-  uint4* q = reinterpret_cast<uint4*>(dst);
-  const uint32_t* w = o.x;  // x then y, contiguous
+template <class F> MSM_D void ba_out(const BaPoints<F>& out, uint32_t k, const typename F::Elem& x, const typename F::Elem& y) {
+  uint32_t wx[F::N], wy[F::N];
+  F::to_packed(x, wx);  // canonical words: an all-zero (x, y) is the identity and nothing else
+  F::to_packed(y, wy);
+  uint4* qx = reinterpret_cast<uint4*>(out.x + (size_t)k * F::N);
+  uint4* qy = reinterpret_cast<uint4*>(out.y + (size_t)k * F::N);
 #pragma unroll
-  for (int j = 0; j < 2 * F::PACKED_WORDS / 4; j++) q[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  for (int j = 0; j < F::N / 4; j++) {
+    qx[j] = make_uint4(wx[4 * j], wx[4 * j + 1], wx[4 * j + 2], wx[4 * j + 3]);
+    qy[j] = make_uint4(wy[4 * j], wy[4 * j + 1], wy[4 * j + 2], wy[4 * j + 3]);
+  }
 }
 
-// One halving round.  off_in / off_out: [NB + 1] exclusive offsets of the buckets in the input and output
-// arrays (off_out = scan of ceil(n_in / 2)).  scratch_prefix: [M_max][T][N words], scratch_idx: [M_max][T],
-// T = gridDim.x * blockDim.x.  Every thread handles ceil(O / T) consecutive outputs, O = off_out[NB].
-// (the body of one thread; also compiled for the host, where tests/test_host_arith.py runs it thread by
-// thread against the oracle -- threads of a round are independent)
+// Position of a thread in the bucket structure while it walks its outputs in increasing order.
+struct BaWalk {
+  uint32_t g, ostart, oend, istart, n_in;
+  bool ready;
+};
+
+// Geometry of a round: O outputs over T threads; a warp owns 32 * per consecutive outputs, lane l of warp w
+// takes k = w * 32 * per + i * 32 + l for i < per.
+struct BaGeom {
+  uint32_t T, O, per;
+};
+MSM_D BaGeom ba_geom(uint32_t T, uint32_t O) {
+  BaGeom gm;
+  gm.T = T;
+  gm.O = O;
+  gm.per = (uint32_t)(((uint64_t)O + T - 1) / T);
+  return gm;
+}
+MSM_D uint64_t ba_item(const BaGeom& gm, uint32_t t, uint32_t i) { return (uint64_t)(t >> 5) * 32 * gm.per + (uint64_t)i * 32 + (t & 31); }
+
+// Forward pass of one batch (items i0 .. i0 + m of thread t): returns the product of the batch's denominators.
 template <class F, bool GATHER>
-MSM_D void ba_round_thread(uint32_t t, uint32_t T, const PackedAffine<F>* __restrict__ src,
-                           const uint32_t* __restrict__ entries, const uint32_t* __restrict__ off_in,
-                           const uint32_t* __restrict__ off_out, uint32_t NB, uint32_t M_max,
-                           PackedAffine<F>* __restrict__ dst, uint32_t* __restrict__ scratch_prefix,
-                           uint32_t* __restrict__ scratch_idx) {
+MSM_D typename F::Elem ba_forward(uint32_t t, const BaGeom& gm, uint32_t i0, uint32_t m, const BaPoints<F>& in,
+                                  const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t NB,
+                                  BaWalk& wk, uint32_t* __restrict__ scratch_prefix, uint32_t* __restrict__ scratch_idx) {
   using E = typename F::Elem;
   constexpr int N = F::N;
-  const uint32_t O = __ldg(off_out + NB);
-  const uint32_t per = (O + T - 1) / T;
-  const uint64_t k_first = (uint64_t)t * per;
-  if (k_first >= O) return;
-  const uint32_t k_last = (uint32_t)(k_first + per < (uint64_t)O ? k_first + per : (uint64_t)O);
-  uint32_t* my_prefix = scratch_prefix + (size_t)t * N;
-  uint32_t* my_idx = scratch_idx + t;
-  const size_t pstride = (size_t)T * N;
-
-  // bucket of the first output: largest g with off_out[g] <= k_first
-  uint32_t g = ba_find_bucket(off_out, NB, (uint32_t)k_first);
-  uint32_t ostart = __ldg(off_out + g), oend = __ldg(off_out + g + 1);
-  uint32_t istart = __ldg(off_in + g), n_in = __ldg(off_in + g + 1) - istart;
-
-  for (uint32_t k0 = (uint32_t)k_first; k0 < k_last; k0 += M_max) {
-    const uint32_t m = M_max < k_last - k0 ? M_max : k_last - k0;
-    // ---------------- forward: denominators and their running product
-    E prefix = F::one();
-    for (uint32_t i = 0; i < m; i++) {
-      const uint32_t k = k0 + i;
-      while (k >= oend) {  // next non-empty bucket
-        g++;
-        ostart = oend;
-        oend = __ldg(off_out + g + 1);
-        istart = __ldg(off_in + g);
-        n_in = __ldg(off_in + g + 1) - istart;
-      }
-      const uint32_t j = k - ostart, a = istart + 2 * j;
-      uint32_t kind = BA_KIND_COPY;
-      if (2 * j + 1 < n_in) {
-        bool na, nb;
-        const PackedAffine<F>* pa = ba_src<F, GATHER>(src, entries, a, na);
-        const PackedAffine<F>* pb = ba_src<F, GATHER>(src, entries, a + 1, nb);
-        const E xa = ba_load_x<F>(pa), xb = ba_load_x<F>(pb);
-        E den = F::template sub<2, 1>(xb, xa);
-        kind = BA_KIND_ADD;
-        if (ba_is_zero<F>(den) || F::is_zero_limbs(xa) || F::is_zero_limbs(xb)) {
-          // rare: equal x (P + P or P - P) or a coordinate that may belong to the identity (0,0)
-          const E ya = ba_load_y<F>(pa, na), yb = ba_load_y<F>(pb, nb);
-          const bool ida = F::is_zero_limbs(xa) && F::is_zero_limbs(ya), idb = F::is_zero_limbs(xb) && F::is_zero_limbs(yb);
-          if (ida || idb) {
-            kind = BA_KIND_SPECIAL;
-          } else if (ba_is_zero<F>(den)) {
-            if (ba_is_zero<F>(F::template sub<2, 1>(yb, ya)) && !ba_is_zero<F>(ya)) {
-              kind = BA_KIND_DBL;
-              den = F::add(ya, ya);
-            } else {
-              kind = BA_KIND_SPECIAL;  // P + (-P), or 2P with y = 0: the identity
-            }
+  E prefix = F::one();
+  for (uint32_t ii = 0; ii < m; ii++) {
+    if (i0 + ii >= gm.per) break;
+    const uint64_t k64 = ba_item(gm, t, i0 + ii);
+    if (k64 >= gm.O) break;  // items grow with ii: nothing further either
+    const uint32_t k = (uint32_t)k64;
+    if (!wk.ready) {
+      wk.g = ba_find_bucket(off_out, NB, k);
+      wk.ostart = __ldg(off_out + wk.g);
+      wk.oend = __ldg(off_out + wk.g + 1);
+      wk.istart = __ldg(off_in + wk.g);
+      wk.n_in = __ldg(off_in + wk.g + 1) - wk.istart;
+      wk.ready = true;
+    }
+    while (k >= wk.oend) {  // next non-empty bucket
+      wk.g++;
+      wk.ostart = wk.oend;
+      wk.oend = __ldg(off_out + wk.g + 1);
+      wk.istart = __ldg(off_in + wk.g);
+      wk.n_in = __ldg(off_in + wk.g + 1) - wk.istart;
+    }
+    const uint32_t j = k - wk.ostart, a = wk.istart + 2 * j;
+    uint32_t kind = BA_KIND_COPY;
+    if (2 * j + 1 < wk.n_in) {
+      const E xa = ba_in_x<F, GATHER>(in, a), xb = ba_in_x<F, GATHER>(in, a + 1);
+      E den = F::template sub<2, 1>(xb, xa);
+      kind = BA_KIND_ADD;
+      if (ba_is_zero<F>(den) || F::is_zero_limbs(xa) || F::is_zero_limbs(xb)) {
+        // rare: equal x (P + P or P - P) or a coordinate that may belong to the identity (0,0)
+        const E ya = ba_in_y<F, GATHER>(in, a), yb = ba_in_y<F, GATHER>(in, a + 1);
+        const bool ida = F::is_zero_limbs(xa) && F::is_zero_limbs(ya), idb = F::is_zero_limbs(xb) && F::is_zero_limbs(yb);
+        if (ida || idb) {
+          kind = BA_KIND_SPECIAL;
+        } else if (ba_is_zero<F>(den)) {
+          if (ba_is_zero<F>(F::template sub<2, 1>(yb, ya)) && !ba_is_zero<F>(ya)) {
+            kind = BA_KIND_DBL;
+            den = F::add(ya, ya);
+          } else {
+            kind = BA_KIND_SPECIAL;  // P + (-P), or 2P with y = 0: the identity
           }
         }
-        if (kind != BA_KIND_SPECIAL) {
-          ba_store_elem<F>(my_prefix + (size_t)i * pstride, prefix);
-          prefix = F::mul(prefix, den);
-        }
       }
-      my_idx[(size_t)i * T] = a | (kind << 30);
+      if (kind != BA_KIND_SPECIAL) {
+        ba_store_elem<F>(scratch_prefix + ((size_t)ii * gm.T + t) * N, prefix);
+        prefix = F::mul(prefix, den);
+      }
     }
-    // ---------------- one inversion for the whole batch
-    E inv = F::inv(prefix);
-    // ---------------- backward: the additions, last item first
-    for (uint32_t i = m; i-- > 0;) {
-      const uint32_t word = my_idx[(size_t)i * T];
-      const uint32_t a = word & 0x3fffffffu, kind = word >> 30;
-      bool na, nb;
-      const PackedAffine<F>* pa = ba_src<F, GATHER>(src, entries, a, na);
-      const E xa = ba_load_x<F>(pa), ya = ba_load_y<F>(pa, na);
-      PackedAffine<F>* out = dst + (k0 + i);
-      if (kind == BA_KIND_COPY) {
-        ba_store_point<F>(out, xa, ya);
-        continue;
-      }
-      const PackedAffine<F>* pb = ba_src<F, GATHER>(src, entries, a + 1, nb);
-      const E xb = ba_load_x<F>(pb), yb = ba_load_y<F>(pb, nb);
-      if (kind == BA_KIND_SPECIAL) {
-        const bool ida = F::is_zero_limbs(xa) && F::is_zero_limbs(ya), idb = F::is_zero_limbs(xb) && F::is_zero_limbs(yb);
-        if (ida) ba_store_point<F>(out, xb, yb);
-        else if (idb) ba_store_point<F>(out, xa, ya);
-        else ba_store_point<F>(out, F::zero(), F::zero());
-        continue;
-      }
-      E den, num;
-      if (kind == BA_KIND_DBL) {
-        den = F::add(ya, ya);
-        const E xx = F::sqr(xa);
-        num = F::add(F::add(xx, xx), xx);
-      } else {
-        den = F::template sub<2, 1>(xb, xa);
-        num = F::template sub<2, 1>(yb, ya);
-      }
-      const E pre = ba_load_elem<F>(my_prefix + (size_t)i * pstride);
-      const E dinv = F::mul(inv, pre);
-      inv = F::mul(inv, den);
-      const E lam = F::mul(num, dinv);
-      const E x3 = F::template sub<2, 1>(F::template sub<2, 1>(F::sqr(lam), xa), xb);
-      const E y3 = F::template sub<2, 1>(F::mul(lam, F::template sub<2, 1>(xa, x3)), ya);
-      ba_store_point<F>(out, x3, y3);
+    scratch_idx[(size_t)ii * gm.T + t] = a | (kind << 30);
+  }
+  return prefix;
+}
+
+// Backward pass of the same batch; inv = 1 / (product returned by ba_forward).
+template <class F, bool GATHER>
+MSM_D void ba_backward(uint32_t t, const BaGeom& gm, uint32_t i0, uint32_t m, const BaPoints<F>& in, const BaPoints<F>& out,
+                       typename F::Elem inv, const uint32_t* __restrict__ scratch_prefix,
+                       const uint32_t* __restrict__ scratch_idx) {
+  using E = typename F::Elem;
+  constexpr int N = F::N;
+  for (uint32_t ii = m; ii-- > 0;) {
+    if (i0 + ii >= gm.per) continue;
+    const uint64_t k64 = ba_item(gm, t, i0 + ii);
+    if (k64 >= gm.O) continue;
+    const uint32_t k = (uint32_t)k64;
+    const uint32_t word = scratch_idx[(size_t)ii * gm.T + t];
+    const uint32_t a = word & 0x3fffffffu, kind = word >> 30;
+    const E xa = ba_in_x<F, GATHER>(in, a), ya = ba_in_y<F, GATHER>(in, a);
+    if (kind == BA_KIND_COPY) {
+      ba_out<F>(out, k, xa, ya);
+      continue;
     }
+    const E xb = ba_in_x<F, GATHER>(in, a + 1), yb = ba_in_y<F, GATHER>(in, a + 1);
+    if (kind == BA_KIND_SPECIAL) {
+      const bool ida = F::is_zero_limbs(xa) && F::is_zero_limbs(ya), idb = F::is_zero_limbs(xb) && F::is_zero_limbs(yb);
+      if (ida) ba_out<F>(out, k, xb, yb);
+      else if (idb) ba_out<F>(out, k, xa, ya);
+      else ba_out<F>(out, k, F::zero(), F::zero());
+      continue;
+    }
+    E den, num;
+    if (kind == BA_KIND_DBL) {
+      den = F::add(ya, ya);
+      const E xx = F::sqr(xa);
+      num = F::add(F::add(xx, xx), xx);
+    } else {
+      den = F::template sub<2, 1>(xb, xa);
+      num = F::template sub<2, 1>(yb, ya);
+    }
+    const E pre = ba_load_elem<F>(scratch_prefix + ((size_t)ii * gm.T + t) * N);
+    const E dinv = F::mul(inv, pre);
+    inv = F::mul(inv, den);
+    const E lam = F::mul(num, dinv);
+    const E x3 = F::template sub<2, 1>(F::template sub<2, 1>(F::sqr(lam), xa), xb);
+    const E y3 = F::template sub<2, 1>(F::mul(lam, F::template sub<2, 1>(xa, x3)), ya);
+    ba_out<F>(out, k, x3, y3);
   }
 }
 
 #if defined(__CUDACC__)
-template <class F, bool GATHER>
-__global__ void __launch_bounds__(BA_BLOCK, (F::N <= 8 ? 3 : 2))
-k_affine_round(const PackedAffine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
-               const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t NB, uint32_t M_max,
-               PackedAffine<F>* __restrict__ dst, uint32_t* __restrict__ scratch_prefix, uint32_t* __restrict__ scratch_idx) {
-  ba_round_thread<F, GATHER>(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, src, entries, off_in, off_out, NB,
-                             M_max, dst, scratch_prefix, scratch_idx);
-}
-
-// counts of the next round from the offsets of this one: n_out[g] = ceil(n_in[g] / 2)
-static __global__ void k_halve_counts(const uint32_t* __restrict__ off_in, uint32_t NB, uint32_t* __restrict__ counts) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < NB) counts[g] = (__ldg(off_in + g + 1) - __ldg(off_in + g) + 1) >> 1;
+// One halving round.  off_in / off_out: [NB + 1] exclusive offsets of the buckets in the input and output
+// arrays (off_out = scan of ceil(n_in / 2)).  scratch_prefix: [M_max][T][N words], scratch_idx: [M_max][T],
+// T = gridDim.x * blockDim.x.
+template <class F, bool GATHER, int BPS>
+__global__ void __launch_bounds__(BA_BLOCK, BPS)
+k_affine_round(BaPoints<F> in, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t NB,
+               uint32_t M_max, BaPoints<F> out, uint32_t* __restrict__ scratch_prefix, uint32_t* __restrict__ scratch_idx) {
+  using E = typename F::Elem;
+  constexpr int N = F::N;
+  __shared__ uint4 tree_raw[2 * BA_BLOCK * N / 4];
+  uint32_t* tree = reinterpret_cast<uint32_t*>(tree_raw);  // node n at tree + n * N; leaves BA_BLOCK .. 2 BA_BLOCK - 1
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x;
+  const BaGeom gm = ba_geom(gridDim.x * blockDim.x, __ldg(off_out + NB));
+  BaWalk wk;
+  wk.ready = false;
+  // the thread that inverts sits in a different warp slot from block to block: the blocks of an SM then do not
+  // queue their inversions on one scheduler
+  const uint32_t inverter = 32u * (blockIdx.x & (BA_BLOCK / 32 - 1));
+  for (uint32_t i0 = 0; i0 < gm.per; i0 += M_max) {  // same trip count for every thread of the grid
+    const E prod = ba_forward<F, GATHER>(t, gm, i0, M_max, in, off_in, off_out, NB, wk, scratch_prefix, scratch_idx);
+    ba_store_elem<F>(tree + (BA_BLOCK + tid) * N, prod);
+    __syncthreads();
+    for (uint32_t s = BA_BLOCK / 2; s >= 1; s >>= 1) {
+      if (tid < s) {
+        const uint32_t n = s + tid;
+        ba_store_elem<F>(tree + n * N, F::mul(ba_load_elem<F>(tree + 2 * n * N), ba_load_elem<F>(tree + (2 * n + 1) * N)));
+      }
+      __syncthreads();
+    }
+    if (tid == inverter) ba_store_elem<F>(tree + N, F::inv(ba_load_elem<F>(tree + N)));
+    __syncthreads();
+    for (uint32_t s = 1; s < BA_BLOCK; s <<= 1) {
+      if (tid < s) {
+        const uint32_t n = s + tid;
+        const E inv_n = ba_load_elem<F>(tree + n * N);
+        const E l = ba_load_elem<F>(tree + 2 * n * N), r = ba_load_elem<F>(tree + (2 * n + 1) * N);
+        ba_store_elem<F>(tree + 2 * n * N, F::mul(inv_n, r));
+        ba_store_elem<F>(tree + (2 * n + 1) * N, F::mul(inv_n, l));
+      }
+      __syncthreads();
+    }
+    const E inv = ba_load_elem<F>(tree + (BA_BLOCK + tid) * N);
+    __syncthreads();  // the tree is rewritten by the next batch
+    ba_backward<F, GATHER>(t, gm, i0, M_max, in, out, inv, scratch_prefix, scratch_idx);
+  }
 }
 #endif
 

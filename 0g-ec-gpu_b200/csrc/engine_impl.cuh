@@ -75,24 +75,6 @@ template <class F> constexpr bool is_bn254() { return F::API_WORDS == 8 || F::AP
 template <class F> constexpr bool is_ext2() { return F::API_WORDS == 16 || F::API_WORDS == 24; }
 template <class F> using BaseParams = typename std::conditional<is_bn254<F>(), Bn254Fq, Bls381Fq>::type;
 
-struct Plan {
-  Geometry geo;
-  uint32_t n_lines, S, n_slices, Q, RW, PG, n_tasks;
-  uint32_t slices_cap;  // upper bound of the slices of one sub-batch
-  uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
-  uint32_t n_sub;   // sub-batches of a pipelined single-task call (they continue one shared bucket array)
-  mutable uint32_t scatter_passes = 1;  // filled in by enqueue_msm (0: two-level partition scatter)
-  bool partition;   // two-level scatter through a (bucket id, entry) temporary, global cursor atomics (measured slower)
-  uint32_t sort_mode;  // 0: single-level atomic sort, 2: binned sort (shared-memory atomics)
-  uint32_t bin_shift;  // binned sort: low bucket-id bits sorted inside a bin
-  uint64_t E_max;
-  size_t scratch_bytes;
-  // affine halving rounds before the XYZZ slice kernel (bucket_affine.cuh); 0: none
-  uint32_t ba_rounds = 0, ba_threads = 0, ba_batch = 0;
-  uint32_t S_tail = 0, n_slices_tail = 0;  // slice geometry of the XYZZ kernel over the points the rounds leave
-  uint64_t ba_cap[2] = {0, 0};             // capacity (points) of the two ping-pong point arrays
-};
-
 // G1 fields on 32-bit limbs only (the Fq2 instantiations have no registers to spare)
 template <class F> constexpr bool ba_supported() { return F::N % 4 == 0 && F::N <= 12 && F::API_WORDS == F::N; }
 
@@ -198,7 +180,11 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   // amortise its inversion (~380 products) and buckets still hold a few entries each.
   pl.ba_rounds = 0;
   if (ba_supported<F>() && n_lines == 1 && pl.E_max < (1ull << 30)) {
-    const uint32_t bps = F::N <= 8 ? 3 : 2;
+    uint32_t bps = F::N <= 8 ? 4 : 2;  // resident blocks per SM (launch bounds of k_affine_round)
+    if (const char* env = getenv("MSM_B200_BA_BPS")) bps = (uint32_t)atoi(env);
+    if (F::N > 8) bps = bps >= 3 ? 3 : 2;
+    else bps = bps >= 4 ? 4 : 3;
+    pl.ba_bps = bps;
     pl.ba_threads = 148u * bps * BA_BLOCK;
     pl.ba_batch = 1024;
     if (const char* env = getenv("MSM_B200_BA_BATCH")) pl.ba_batch = (uint32_t)std::max(16, atoi(env));
@@ -234,125 +220,6 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     }
   }
   pl.scratch_bytes = b;
-  return MSM_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// The three sorts (kernels.cuh).  All leave bucket_start[NB+1] (exclusive scan of the bucket sizes,
-// bucket_start[NB] = number of non-zero digits) and the entries in bucket order.  sg is the geometry
-// of the (sub-)batch, E_max its digit bound; temporaries come from the scratch arena.
-// ---------------------------------------------------------------------------------------------
-struct SortBuffers {
-  uint32_t *counts, *bucket_start, *cursor, *tile_sums, *entries;
-};
-
-inline void enqueue_bucket_scan(cudaStream_t st, const Geometry& g, const SortBuffers& b) {
-  const uint32_t n_tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
-  k_scan_tiles<<<n_tiles, SCAN_BLOCK, 0, st>>>(b.counts, g.NB, b.bucket_start, b.tile_sums);
-  k_scan_tile_sums<<<1, SCAN_BLOCK, 0, st>>>(b.tile_sums, n_tiles, b.tile_sums + n_tiles);
-  k_scan_finish<<<(g.NB + 1 + 255) / 256, 256, 0, st>>>(b.bucket_start, g.NB, b.tile_sums, b.tile_sums + n_tiles, b.cursor);
-}
-
-// digits staged per k_partition block (8 bytes each in shared memory): measured best of 6144 .. 12288
-inline uint32_t partition_tile(uint32_t W) {
-  uint32_t part_entries = 12288;
-  if (const char* env = getenv("MSM_B200_PART_ENTRIES")) part_entries = (uint32_t)atoi(env);
-  const uint32_t tile = part_entries / W;
-  return tile > 1024 ? 1024 : (tile < 64 ? 64 : tile);
-}
-
-// Binned sort: every per-digit atomic in shared memory (large calls).
-inline int enqueue_sort_binned(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                               const uint32_t* scalars, const SortBuffers& b) {
-  cudaStream_t st = dc.stream;
-  CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
-  if (sg.L == 0) {
-    enqueue_bucket_scan(st, sg, b);
-    return MSM_OK;
-  }
-  const size_t cap = pl.E_max / pl.n_sub + sg.W;
-  uint32_t* tmp_g = dc.arena.take<uint32_t>(cap);
-  uint32_t* tmp_v = dc.arena.take<uint32_t>(cap);
-  uint32_t* bin_count = dc.arena.take<uint32_t>(1024);  // [bin_count | bin_cursor]: one memset
-  uint32_t* bin_cursor = dc.arena.take<uint32_t>(1024);
-  uint32_t* bin_start = dc.arena.take<uint32_t>(1025);
-  uint32_t* tile_start = dc.arena.take<uint32_t>(1025);
-  const uint32_t bin_shift = pl.bin_shift;
-  const uint32_t n_bins = (uint32_t)(((uint64_t)sg.NB + (1ull << bin_shift) - 1) >> bin_shift);
-  CU_TRY(ctx, cudaMemsetAsync(bin_count, 0, (size_t)((char*)bin_start - (char*)bin_count), st));
-  launch_bin_count((sg.L + BIN_COUNT_SCALARS - 1) / BIN_COUNT_SCALARS, st, scalars, sg, bin_shift, n_bins, bin_count);
-  k_bin_scan<<<1, SCAN_BLOCK, 0, st>>>(bin_count, n_bins, bin_start, tile_start);
-  const uint32_t tile = partition_tile(sg.W);
-  const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * sg.W) * 4;
-  CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, scalars, sg, tile, bin_shift, n_bins, bin_start, 0u,
-                               bin_cursor, tmp_g, tmp_v));
-  const uint32_t max_tiles = (uint32_t)(E_max / BIN_TILE) + n_bins + 1;
-  k_bin_hist<<<max_tiles, BIN_BLOCK, (size_t)4 << bin_shift, st>>>(tmp_g, bin_start, tile_start, n_bins, bin_shift, sg.NB,
-                                                                  b.counts);
-  enqueue_bucket_scan(st, sg, b);
-  const size_t psmem = bin_place_smem(bin_shift);
-  CU_TRY(ctx, cudaFuncSetAttribute(k_bin_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-  k_bin_place<<<max_tiles, PLACE_BLOCK, psmem, st>>>(tmp_g, tmp_v, bin_start, tile_start, n_bins, bin_shift, sg.NB, b.cursor,
-                                                    b.entries);
-  pl.scatter_passes = 0;
-  dc.launches += 5;
-  return MSM_OK;
-}
-
-// Two-level scatter with global cursor atomics in the second level (MSM_B200_PARTITION=1: measured slower
-// than both other sorts, kept as evidence).
-inline int enqueue_sort_partition(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                                  const uint32_t* scalars, const SortBuffers& b) {
-  cudaStream_t st = dc.stream;
-  CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
-  const uint32_t db = 256, dg = (sg.L + db - 1) / db;
-  if (dg) launch_digits<false>(dg, db, st, scalars, sg, b.counts, nullptr, 0u, sg.NB);
-  enqueue_bucket_scan(st, sg, b);
-  if (!dg) return MSM_OK;
-  const size_t cap = pl.E_max / pl.n_sub + sg.W;
-  uint32_t* tmp_g = dc.arena.take<uint32_t>(cap);
-  uint32_t* tmp_v = dc.arena.take<uint32_t>(cap);
-  uint32_t* bin_cursor = dc.arena.take<uint32_t>(4096);
-  uint32_t bins = 16;
-  while (bins < 1024 && (uint64_t)bins * (4u << 20) < E_max * 4) bins <<= 1;  // ~4 MB of entries per bin
-  uint32_t nb_log = 0;
-  while ((1ull << nb_log) < sg.NB) nb_log++;
-  uint32_t bins_log = 0;
-  while ((1u << bins_log) < bins) bins_log++;
-  const uint32_t bin_shift = nb_log > bins_log ? nb_log - bins_log : 0;
-  const uint32_t n_bins = (uint32_t)(((uint64_t)sg.NB + (1ull << bin_shift) - 1) >> bin_shift);
-  const uint32_t tile = partition_tile(sg.W);
-  const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * sg.W) * 4;
-  CU_TRY(ctx, cudaMemsetAsync(bin_cursor, 0, (size_t)n_bins * 4, st));
-  CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, scalars, sg, tile, bin_shift, n_bins, b.bucket_start,
-                               bin_shift, bin_cursor, tmp_g, tmp_v));
-  k_final_scatter<<<(uint32_t)((E_max + 255) / 256), 256, 0, st>>>(tmp_g, tmp_v, b.bucket_start + sg.NB, b.cursor, b.entries);
-  pl.scatter_passes = 0;
-  dc.launches += 2;
-  return MSM_OK;
-}
-
-// Single-level sort: one L2 atomic per digit in the histogram and in the scatter (small calls).  The
-// scatter runs in bucket-range passes: each pass writes a bounded slice of `entries` at random, which the
-// 126 MB L2 partly absorbs; every pass re-reads the scalars (sequential).
-inline int enqueue_sort_atomic(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                               const uint32_t* scalars, const SortBuffers& b) {
-  cudaStream_t st = dc.stream;
-  CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
-  const uint32_t db = 256, dg = (sg.L + db - 1) / db;
-  if (dg) launch_digits<false>(dg, db, st, scalars, sg, b.counts, nullptr, 0u, sg.NB);
-  enqueue_bucket_scan(st, sg, b);
-  uint32_t passes = (uint32_t)((E_max * 4 + (200u << 20) - 1) / (200u << 20));
-  if (const char* env = getenv("MSM_B200_SCATTER_PASSES")) passes = (uint32_t)atoi(env);
-  passes = passes < 1 ? 1 : (passes > 8 ? 8 : passes);
-  pl.scatter_passes = passes;
-  const uint32_t per = (sg.NB + passes - 1) / passes;
-  for (uint32_t ps = 0; ps < passes && dg; ps++) {
-    const uint32_t lo = ps * per, hi = lo + per < sg.NB ? lo + per : sg.NB;
-    if (lo >= hi) break;
-    launch_digits<true>(dg, db, st, scalars, sg, b.cursor, b.entries, lo, hi);
-    dc.launches += 1;
-  }
   return MSM_OK;
 }
 
@@ -431,24 +298,30 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     bool ba_done = false;
     if constexpr (ba_supported<F>()) {
       if (pl.ba_rounds) {
-        // affine halving rounds (bucket_affine.cuh): entries -> points[0] -> points[1] -> points[0] ...
-        PackedAffine<F>* pts[2] = {dc.arena.take<PackedAffine<F>>(pl.ba_cap[0]), dc.arena.take<PackedAffine<F>>(pl.ba_cap[1])};
+        // affine halving rounds (bucket_affine.cuh): entries -> planes[0] -> planes[1] -> planes[0] ...
+        constexpr size_t NW = F::N;
+        uint32_t* planes[2] = {dc.arena.take<uint32_t>(2 * pl.ba_cap[0] * NW), dc.arena.take<uint32_t>(2 * pl.ba_cap[1] * NW)};
         uint32_t* offs[2] = {dc.arena.take<uint32_t>(g.NB + 1), dc.arena.take<uint32_t>(g.NB + 1)};
         uint32_t* sc_prefix = dc.arena.take<uint32_t>((size_t)pl.ba_threads * pl.ba_batch * F::N);
         uint32_t* sc_idx = dc.arena.take<uint32_t>((size_t)pl.ba_threads * pl.ba_batch);
         const uint32_t* off_in = bucket_start;
         const uint32_t ba_grid = pl.ba_threads / BA_BLOCK;
+        BaPoints<F> pin{bases_sb, entries, nullptr, nullptr};
         for (uint32_t r = 0; r < pl.ba_rounds; r++) {
           uint32_t* off_out = offs[r & 1];
-          k_halve_counts<<<(g.NB + 255) / 256, 256, 0, st>>>(off_in, g.NB, counts);
           const SortBuffers hb{counts, off_out, cursor, tile_sums, nullptr};
-          enqueue_bucket_scan(st, g, hb);
-          if (r == 0)
-            k_affine_round<F, true><<<ba_grid, BA_BLOCK, 0, st>>>(bases_sb, entries, off_in, off_out, g.NB, pl.ba_batch,
-                                                                 pts[0], sc_prefix, sc_idx);
+          enqueue_halve_scan(st, g, off_in, hb);
+          BaPoints<F> pout{nullptr, nullptr, planes[r & 1], planes[r & 1] + pl.ba_cap[r & 1] * NW};
+          constexpr int BPS_LO = F::N <= 8 ? 3 : 2, BPS_HI = BPS_LO + 1;
+          if (r == 0 && pl.ba_bps == BPS_HI)
+            k_affine_round<F, true, BPS_HI><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, g.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
+          else if (r == 0)
+            k_affine_round<F, true, BPS_LO><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, g.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
+          else if (pl.ba_bps == BPS_HI)
+            k_affine_round<F, false, BPS_HI><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, g.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
           else
-            k_affine_round<F, false><<<ba_grid, BA_BLOCK, 0, st>>>(pts[(r - 1) & 1], nullptr, off_in, off_out, g.NB,
-                                                                  pl.ba_batch, pts[r & 1], sc_prefix, sc_idx);
+            k_affine_round<F, false, BPS_LO><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, g.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
+          pin = pout;
           off_in = off_out;
           dc.launches += 5;
         }
@@ -456,14 +329,15 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
         S = pl.S_tail;
         n_slices = pl.n_slices_tail;
         grid = dim3((n_slices + tb - 1) / tb, 1);
-        k_accumulate<F><<<grid, tb, 0, st>>>(pts[(pl.ba_rounds - 1) & 1], 0u, nullptr, acc_starts, g.NB, acc_starts + g.NB, S,
-                                             n_slices, acc_sb, partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap);
+        k_accumulate<F><<<grid, tb, 0, st>>>(nullptr, 0u, nullptr, acc_starts, g.NB, acc_starts + g.NB, S, n_slices, acc_sb,
+                                             partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap, pin.x, pin.y);
         ba_done = true;
       }
     }
     if (!ba_done)
       k_accumulate<F><<<grid, tb, 0, st>>>(bases_sb, line_stride, entries, bucket_start, g.NB, bucket_start + g.NB,
-                                           S, n_slices, acc_sb, partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap);
+                                           S, n_slices, acc_sb, partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap,
+                                           nullptr, nullptr);
     // at most one cut bucket per slice
     k_fixup_cut<F><<<grid, tb, 0, st>>>(acc_starts, g.NB, S, n_slices, acc_sb, partials, fl);
     const uint32_t hblocks = (fl.chunk_cap + 3) / 4;

@@ -20,88 +20,11 @@
 // chunk serially against buckets in global memory.
 #pragma once
 #include "ec.cuh"
+#include "sort.h"
 
 namespace msm {
 
-struct Geometry {
-  uint32_t L;          // scalars per row actually used (= num_chunks * chunk_len)
-  uint32_t chunk_len;  // points per task
-  uint32_t num_chunks; // scalar-side tasks
-  uint32_t c;          // window bits
-  uint32_t W;          // windows
-  uint32_t B;          // buckets per (task, window) = 2^(c-1)
-  uint32_t NB;         // num_chunks * W * B   (folded: num_chunks * B)
-  uint32_t scalar_bits;
-  uint32_t fold;       // 1: bases are a window table T[w][i] = 2^(c w) P_i, all windows of a task share one bucket set
-  uint32_t table_stride;  // points per window in the table (= points of the resident shard)
-  uint32_t point_offset;  // folded sub-batches: index of this batch's first point in the table
-};
-MSM_HD uint32_t task_of(uint32_t i, const Geometry& geo) { return geo.num_chunks == 1 ? 0u : i / geo.chunk_len; }
-
-// ---------------------------------------------------------------------------------------------
-// Signed-digit decomposition.  k = sum_w d_w 2^(c w),  d_w in [-(2^(c-1) - 1), 2^(c-1)].
-// W*c >= scalar_bits + 1 guarantees no carry out of the top window (the reference's kernel drops
-// that carry, TODO at ag-build/cl/multiexp.cl:60).  Bits are taken LSB-first from the canonical
-// little-endian scalar (the reference indexes MSB-first, ag-build/cl/field.cl:380-392; the digit
-// set is a free choice because the result does not depend on it).
-// f(w, bucket_1based, negative) is called for every non-zero digit.
-// ---------------------------------------------------------------------------------------------
-template <class F> MSM_D void for_each_digit(const uint32_t k[8], uint32_t c, uint32_t W, F&& f) {
-  const uint32_t half = 1u << (c - 1);
-  const uint32_t mask = (1u << c) - 1u;
-  uint64_t buf = 0;
-  uint32_t nbits = 0, w = 0, carry = 0;
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    buf |= (uint64_t)k[j] << nbits;
-    nbits += 32;
-    while (nbits >= c && w < W) {
-      uint32_t raw = ((uint32_t)buf & mask) + carry;
-      buf >>= c;
-      nbits -= c;
-      carry = raw > half;
-      if (raw != 0 && raw != (1u << c)) {
-        if (carry) f(w, (1u << c) - raw, true);
-        else f(w, raw, false);
-      }
-      w++;
-    }
-  }
-  // remaining high bits (fewer than c)
-  while (w < W) {
-    uint32_t raw = ((uint32_t)buf & mask) + carry;
-    buf >>= c;
-    carry = raw > half;
-    if (raw != 0 && raw != (1u << c)) {
-      if (carry) f(w, (1u << c) - raw, true);
-      else f(w, raw, false);
-    }
-    w++;
-  }
-}
-
-// Same decomposition with the window size known at compile time: every digit is one funnel shift
-// and one mask on registers (the generic loop above spends ~3x the instructions on 64-bit buffer
-// shifts; with 4-5 decomposition passes per call that was ~2 ms of a 2^24 MSM).
-template <int C, class F> MSM_D void for_each_digit_c(const uint32_t k[8], uint32_t W, F&& f) {
-  constexpr uint32_t half = 1u << (C - 1);
-  constexpr uint32_t mask = (1u << C) - 1u;
-  constexpr int MAXW = (256 + C - 1) / C + 1;
-  uint32_t carry = 0;
-#pragma unroll
-  for (int w = 0; w < MAXW; w++) {
-    if ((uint32_t)w >= W) break;
-    const int bit = w * C, word = bit >> 5, sh = bit & 31;
-    const uint32_t lo = word < 8 ? k[word < 8 ? word : 0] : 0u;
-    const uint32_t hi = word + 1 < 8 ? k[word + 1 < 8 ? word + 1 : 0] : 0u;
-    const uint32_t raw = (__funnelshift_r(lo, hi, sh) & mask) + carry;
-    carry = raw > half;
-    if (raw != 0 && raw != (1u << C)) {
-      if (carry) f((uint32_t)w, (1u << C) - raw, true);
-      else f((uint32_t)w, raw, false);
-    }
-  }
-}
+// Geometry, Plan and the sort entry points live in sort.h (the sort is field-independent: one unit, sort.cu)
 
 MSM_D void load_scalar(const uint32_t* scalars, uint32_t i, uint32_t k[8]) {
   const uint4* p = reinterpret_cast<const uint4*>(scalars) + 2 * (size_t)i;
@@ -109,484 +32,6 @@ MSM_D void load_scalar(const uint32_t* scalars, uint32_t i, uint32_t k[8]) {
   k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
   k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
 }
-
-// SCATTER = false: counts[g]++ ;  SCATTER = true: entries[cursor[g]++] = i | sign<<31
-// g_lo / g_hi: only digits whose bucket id lies in [g_lo, g_hi) are handled; the scatter runs in
-// several such passes so that the randomly written slice of `entries` stays resident in the L2.
-template <bool SCATTER, int C>
-__global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
-                         uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries,
-                         uint32_t g_lo, uint32_t g_hi) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= geo.L) return;
-  uint32_t k[8];
-  load_scalar(scalars, i, k);
-  const uint32_t task = i / geo.chunk_len;
-  const uint32_t base = task * geo.W;
-  auto body = [&](uint32_t w, uint32_t bucket, bool neg) {
-    const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
-    if (g < g_lo || g >= g_hi) return;
-    // The top window only carries the few leftover scalar bits, so all points share a handful of
-    // its buckets: aggregate those atomics per warp (one atomic per distinct bucket).
-    uint32_t rank = 0, total = 1, leader_lane = 0;
-    const bool aggregate = (w + 1 == geo.W);
-    uint32_t peers = 0;
-    if (aggregate) {
-      peers = __match_any_sync(__activemask(), g);
-      leader_lane = __ffs(peers) - 1;
-      total = __popc(peers);
-      rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
-    }
-    if (SCATTER) {
-      uint32_t pos;
-      if (aggregate) {
-        uint32_t base_pos = 0;
-        if ((threadIdx.x & 31) == leader_lane) base_pos = atomicAdd(&counts_or_cursor[g], total);
-        pos = __shfl_sync(peers, base_pos, leader_lane) + rank;
-      } else {
-        pos = atomicAdd(&counts_or_cursor[g], 1u);
-      }
-      const uint32_t idx = geo.fold ? w * geo.table_stride + geo.point_offset + i : i;
-      entries[pos] = idx | (neg ? 0x80000000u : 0u);
-    } else {
-      if (!aggregate) atomicAdd(&counts_or_cursor[g], 1u);
-      else if ((threadIdx.x & 31) == leader_lane) atomicAdd(&counts_or_cursor[g], total);
-    }
-  };
-  if (C == 0) for_each_digit(k, geo.c, geo.W, body);
-  else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
-}
-
-// launch with the window size as a template argument where an instantiation exists
-template <bool SCATTER>
-inline void launch_digits(uint32_t grid, uint32_t block, cudaStream_t st, const uint32_t* scalars, const Geometry& geo,
-                          uint32_t* counts_or_cursor, uint32_t* entries, uint32_t g_lo, uint32_t g_hi) {
-#define MSM_DIGITS_CASE(CC) \
-  case CC: k_digits<SCATTER, CC><<<grid, block, 0, st>>>(scalars, geo, counts_or_cursor, entries, g_lo, g_hi); break;
-  switch (geo.c) {
-    MSM_DIGITS_CASE(6) MSM_DIGITS_CASE(7) MSM_DIGITS_CASE(8) MSM_DIGITS_CASE(9) MSM_DIGITS_CASE(10)
-    MSM_DIGITS_CASE(11) MSM_DIGITS_CASE(12) MSM_DIGITS_CASE(13) MSM_DIGITS_CASE(14) MSM_DIGITS_CASE(15)
-    MSM_DIGITS_CASE(16) MSM_DIGITS_CASE(17) MSM_DIGITS_CASE(18) MSM_DIGITS_CASE(19) MSM_DIGITS_CASE(20)
-    MSM_DIGITS_CASE(21) MSM_DIGITS_CASE(22) MSM_DIGITS_CASE(23) MSM_DIGITS_CASE(24)
-    default: k_digits<SCATTER, 0><<<grid, block, 0, st>>>(scalars, geo, counts_or_cursor, entries, g_lo, g_hi);
-  }
-#undef MSM_DIGITS_CASE
-}
-
-// ---------------------------------------------------------------------------------------------
-// Exclusive scan of n uint32 (three small kernels; n <= a few million, HBM-trivial).
-// ---------------------------------------------------------------------------------------------
-constexpr int SCAN_BLOCK = 256;
-constexpr int SCAN_ITEMS = 8;  // per thread
-constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
-
-template <int BS> __device__ __forceinline__ uint32_t block_exclusive_scan_t(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t warp_sums[BS / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t x = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) warp_sums[wid] = x;
-  __syncthreads();
-  if (wid == 0) {
-    uint32_t s = lane < BS / 32 ? warp_sums[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < BS / 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += y;
-    }
-    if (lane < BS / 32) warp_sums[lane] = s;
-  }
-  __syncthreads();
-  const uint32_t warp_off = wid ? warp_sums[wid - 1] : 0;
-  *total = warp_sums[BS / 32 - 1];
-  __syncthreads();
-  return warp_off + x - v;
-}
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
-  return block_exclusive_scan_t<SCAN_BLOCK>(v, total);
-}
-
-static __global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
-                             uint32_t* __restrict__ tile_sums) {
-  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  uint32_t v[SCAN_ITEMS], s = 0;
-#pragma unroll
-  for (int j = 0; j < SCAN_ITEMS; j++) {
-    v[j] = base + j < n ? in[base + j] : 0;
-    s += v[j];
-  }
-  uint32_t total;
-  uint32_t off = block_exclusive_scan(s, &total);
-#pragma unroll
-  for (int j = 0; j < SCAN_ITEMS; j++) {
-    if (base + j < n) out[base + j] = off;
-    off += v[j];
-  }
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-// single block: exclusive scan of tile sums in place, total written to *grand_total
-static __global__ void k_scan_tile_sums(uint32_t* tile_sums, uint32_t n_tiles, uint32_t* grand_total) {
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < n_tiles; base += SCAN_BLOCK) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < n_tiles ? tile_sums[i] : 0;
-    uint32_t total;
-    uint32_t off = block_exclusive_scan(v, &total);
-    if (i < n_tiles) tile_sums[i] = carry + off;
-    carry += total;
-  }
-  if (threadIdx.x == 0) *grand_total = carry;
-}
-// out[i] += tile_offset; also writes the closing element out[n] = grand_total and a copy (cursor)
-static __global__ void k_scan_finish(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_sums,
-                              const uint32_t* __restrict__ grand_total, uint32_t* __restrict__ cursor) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    uint32_t v = out[i] + tile_sums[i / SCAN_TILE];
-    out[i] = v;
-    cursor[i] = v;
-  } else if (i == n) {
-    out[n] = *grand_total;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Two-level scatter (large calls).  A single-pass scatter writes 4-byte entries at random over
-// hundreds of MB: every write costs a 32-byte sector of DRAM traffic.  Instead:
-//   k_partition      each block decomposes a tile of scalars, groups its digits by the HIGH bits
-//                    of the bucket id in shared memory and appends every group to that high-bin's
-//                    region of a temporary (bucket id, entry) array in coalesced runs;
-//   k_final_scatter  walks the temporary array (now ordered by high-bin) and places every entry
-//                    with the usual cursor atomic -- the cursors and the destination slice touched
-//                    at any moment are a few MB and stay in the L2.
-// hb = g >> bin_shift; hb_region[hb] = bucket_start[hb << bin_shift] is where bin hb starts.
-// ---------------------------------------------------------------------------------------------
-constexpr int PART_BLOCK = 512;
-template <int C>
-__global__ void __launch_bounds__(PART_BLOCK)
-k_partition(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t tile, uint32_t bin_shift, uint32_t n_bins,
-            const uint32_t* __restrict__ region_start, uint32_t region_shift, uint32_t* __restrict__ bin_cursor,
-            uint32_t* __restrict__ tmp_g, uint32_t* __restrict__ tmp_v) {
-  extern __shared__ uint32_t part_smem[];
-  uint32_t* hist = part_smem;                 // [n_bins] counts, then running cursors
-  uint32_t* off = hist + n_bins;              // [n_bins] exclusive offsets inside the block
-  uint32_t* gbase = off + n_bins;             // [n_bins] global base of this block's run
-  uint32_t* stage_g = gbase + n_bins;         // [tile * W]
-  uint32_t* stage_v = stage_g + (size_t)tile * geo.W;
-  __shared__ uint32_t total_sh;
-  const uint32_t first = blockIdx.x * tile;
-  for (uint32_t b = threadIdx.x; b < n_bins; b += PART_BLOCK) hist[b] = 0;
-  __syncthreads();
-  // pass 1: histogram of high bins
-  for (uint32_t t = threadIdx.x; t < tile; t += PART_BLOCK) {
-    const uint32_t i = first + t;
-    if (i >= geo.L) break;
-    uint32_t k[8];
-    load_scalar(scalars, i, k);
-    const uint32_t base = (i / geo.chunk_len) * geo.W;
-    auto body = [&](uint32_t w, uint32_t bucket, bool) {
-      const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
-      atomicAdd(&hist[g >> bin_shift], 1u);
-    };
-    if (C == 0) for_each_digit(k, geo.c, geo.W, body);
-    else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
-  }
-  __syncthreads();
-  // exclusive scan of the bins (n_bins <= 4 * PART_BLOCK), one global reservation per non-empty bin
-  {
-    uint32_t v[4], sum = 0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const uint32_t b = threadIdx.x * 4 + q;
-      v[q] = b < n_bins ? hist[b] : 0;
-      sum += v[q];
-    }
-    uint32_t total;
-    uint32_t run = block_exclusive_scan_t<PART_BLOCK>(sum, &total);
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const uint32_t b = threadIdx.x * 4 + q;
-      if (b < n_bins) {
-        off[b] = run;
-        gbase[b] = v[q] ? region_start[b << region_shift] + atomicAdd(&bin_cursor[b], v[q]) : 0;
-        hist[b] = 0;
-      }
-      run += v[q];
-    }
-    if (threadIdx.x == 0) total_sh = total;
-  }
-  __syncthreads();
-  // pass 2: same decomposition, place (g, entry) in the block-local bin order
-  for (uint32_t t = threadIdx.x; t < tile; t += PART_BLOCK) {
-    const uint32_t i = first + t;
-    if (i >= geo.L) break;
-    uint32_t k[8];
-    load_scalar(scalars, i, k);
-    const uint32_t base = (i / geo.chunk_len) * geo.W;
-    auto body = [&](uint32_t w, uint32_t bucket, bool neg) {
-      const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
-      const uint32_t hb = g >> bin_shift;
-      const uint32_t slot = off[hb] + atomicAdd(&hist[hb], 1u);
-      const uint32_t idx = geo.fold ? w * geo.table_stride + geo.point_offset + i : i;
-      stage_g[slot] = g;
-      stage_v[slot] = idx | (neg ? 0x80000000u : 0u);
-    };
-    if (C == 0) for_each_digit(k, geo.c, geo.W, body);
-    else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
-  }
-  __syncthreads();
-  // write every bin's run to its region: consecutive slots of one bin are consecutive in memory
-  const uint32_t total = total_sh;
-  for (uint32_t sidx = threadIdx.x; sidx < total; sidx += PART_BLOCK) {
-    const uint32_t g = stage_g[sidx];
-    const uint32_t hb = g >> bin_shift;
-    const uint32_t dst = gbase[hb] + (sidx - off[hb]);
-    tmp_g[dst] = g;
-    tmp_v[dst] = stage_v[sidx];
-  }
-}
-
-static __global__ void k_final_scatter(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp_v,
-                                       const uint32_t* __restrict__ E_ptr, uint32_t* __restrict__ cursor,
-                                       uint32_t* __restrict__ entries) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= __ldg(E_ptr)) return;
-  const uint32_t pos = atomicAdd(&cursor[__ldg(tmp_g + i)], 1u);
-  entries[pos] = __ldg(tmp_v + i);
-}
-
-template <int C> inline cudaError_t partition_set_smem(size_t bytes) {
-  return cudaFuncSetAttribute(k_partition<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-inline cudaError_t launch_partition(uint32_t grid, size_t smem, cudaStream_t st, const uint32_t* scalars,
-                                    const Geometry& geo, uint32_t tile, uint32_t bin_shift, uint32_t n_bins,
-                                    const uint32_t* region_start, uint32_t region_shift, uint32_t* bin_cursor,
-                                    uint32_t* tmp_g, uint32_t* tmp_v) {
-  cudaError_t e = cudaSuccess;
-#define MSM_PART_CASE(CC)                                                                                        \
-  case CC:                                                                                                       \
-    e = partition_set_smem<CC>(smem);                                                                            \
-    if (e == cudaSuccess)                                                                                        \
-      k_partition<CC><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, region_start,       \
-                                                      region_shift, bin_cursor, tmp_g, tmp_v);                   \
-    break;
-  switch (geo.c) {
-    MSM_PART_CASE(16) MSM_PART_CASE(17) MSM_PART_CASE(18) MSM_PART_CASE(19) MSM_PART_CASE(20)
-    MSM_PART_CASE(21) MSM_PART_CASE(22) MSM_PART_CASE(23) MSM_PART_CASE(24)
-    default:
-      e = partition_set_smem<0>(smem);
-      if (e == cudaSuccess)
-        k_partition<0><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, region_start, region_shift,
-                                                       bin_cursor, tmp_g, tmp_v);
-  }
-#undef MSM_PART_CASE
-  return e;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Binned sort (large calls): the same two levels, with every per-digit atomic in SHARED memory.
-// The L2 executes ~80 atomics per clock for the whole chip; a 2^24-point call needs 4 x 10^8 of
-// them in the single-level sort above (histogram + scatter) and that is what its 4.9 ms are.  Here:
-//   k_bin_count   coarse histogram (bins = high bits of the bucket id), per-block in shared memory
-//   k_bin_scan    bin offsets, and the number of fixed-size tiles each bin is cut into
-//   k_partition   (above) groups the digits by bin into tmp_g / tmp_v in coalesced runs
-//   k_bin_hist    one block per tile of one bin: shared-memory histogram of the low bits, then one
-//                 global add per non-empty bucket of the tile
-//   (scan)        bucket_start / cursor as before
-//   k_bin_place   one block per tile: reserves the tile's range of every bucket with one atomic per
-//                 non-empty bucket, then places the entries with shared-memory cursors; the writes
-//                 of a tile land in the few hundred KB of its bin's slice of `entries`
-// Tiles make skewed inputs (and the short top window of a folded table, whose digits all fall into
-// the first bins) a matter of more blocks, not of longer ones.
-// ---------------------------------------------------------------------------------------------
-constexpr uint32_t BIN_TILE = 16384;
-constexpr int BIN_BLOCK = 256;
-constexpr uint32_t BIN_COUNT_SCALARS = 2048;  // scalars per block in k_bin_count
-
-template <int C>
-__global__ void __launch_bounds__(BIN_BLOCK)
-k_bin_count(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t bin_shift, uint32_t n_bins,
-            uint32_t* __restrict__ bin_count) {
-  extern __shared__ uint32_t bin_smem[];
-  for (uint32_t b = threadIdx.x; b < n_bins; b += BIN_BLOCK) bin_smem[b] = 0;
-  __syncthreads();
-  const uint32_t first = blockIdx.x * BIN_COUNT_SCALARS;
-  for (uint32_t t = threadIdx.x; t < BIN_COUNT_SCALARS; t += BIN_BLOCK) {
-    const uint32_t i = first + t;
-    if (i >= geo.L) break;
-    uint32_t k[8];
-    load_scalar(scalars, i, k);
-    const uint32_t base = (i / geo.chunk_len) * geo.W;
-    auto body = [&](uint32_t w, uint32_t bucket, bool) {
-      const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
-      atomicAdd(&bin_smem[g >> bin_shift], 1u);
-    };
-    if (C == 0) for_each_digit(k, geo.c, geo.W, body);
-    else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
-  }
-  __syncthreads();
-  for (uint32_t b = threadIdx.x; b < n_bins; b += BIN_BLOCK)
-    if (bin_smem[b]) atomicAdd(&bin_count[b], bin_smem[b]);
-}
-inline void launch_bin_count(uint32_t grid, cudaStream_t st, const uint32_t* scalars, const Geometry& geo,
-                             uint32_t bin_shift, uint32_t n_bins, uint32_t* bin_count) {
-  const size_t smem = (size_t)n_bins * 4;
-#define MSM_BINC_CASE(CC) \
-  case CC: k_bin_count<CC><<<grid, BIN_BLOCK, smem, st>>>(scalars, geo, bin_shift, n_bins, bin_count); break;
-  switch (geo.c) {
-    MSM_BINC_CASE(8) MSM_BINC_CASE(9) MSM_BINC_CASE(10) MSM_BINC_CASE(11) MSM_BINC_CASE(12) MSM_BINC_CASE(13)
-    MSM_BINC_CASE(14) MSM_BINC_CASE(15) MSM_BINC_CASE(16) MSM_BINC_CASE(17) MSM_BINC_CASE(18) MSM_BINC_CASE(19)
-    MSM_BINC_CASE(20) MSM_BINC_CASE(21) MSM_BINC_CASE(22) MSM_BINC_CASE(23) MSM_BINC_CASE(24)
-    default: k_bin_count<0><<<grid, BIN_BLOCK, smem, st>>>(scalars, geo, bin_shift, n_bins, bin_count);
-  }
-#undef MSM_BINC_CASE
-}
-
-// single block; n_bins <= 4 * SCAN_BLOCK.  bin_start / tile_start have n_bins + 1 elements.
-static __global__ void k_bin_scan(const uint32_t* __restrict__ bin_count, uint32_t n_bins,
-                                  uint32_t* __restrict__ bin_start, uint32_t* __restrict__ tile_start) {
-  uint32_t c[4], tl[4], sc = 0, stl = 0;
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const uint32_t b = threadIdx.x * 4 + q;
-    c[q] = b < n_bins ? bin_count[b] : 0;
-    tl[q] = (c[q] + BIN_TILE - 1) / BIN_TILE;
-    sc += c[q];
-    stl += tl[q];
-  }
-  uint32_t total_c, total_t;
-  uint32_t off_c = block_exclusive_scan(sc, &total_c);
-  uint32_t off_t = block_exclusive_scan(stl, &total_t);
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const uint32_t b = threadIdx.x * 4 + q;
-    if (b < n_bins) {
-      bin_start[b] = off_c;
-      tile_start[b] = off_t;
-    }
-    off_c += c[q];
-    off_t += tl[q];
-  }
-  if (threadIdx.x == 0) {
-    bin_start[n_bins] = total_c;
-    tile_start[n_bins] = total_t;
-  }
-}
-
-// which bin does tile `tile` belong to, and which entries of tmp_* does it cover
-MSM_D bool bin_tile_range(const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ tile_start,
-                          uint32_t n_bins, uint32_t tile, uint32_t& bin, uint32_t& lo, uint32_t& hi) {
-  if (tile >= __ldg(tile_start + n_bins)) return false;
-  uint32_t a = 0, b = n_bins;  // invariant: tile_start[a] <= tile < tile_start[b]
-  while (b - a > 1) {
-    const uint32_t mid = (a + b) >> 1;
-    if (__ldg(tile_start + mid) <= tile) a = mid;
-    else b = mid;
-  }
-  bin = a;
-  lo = __ldg(bin_start + a) + (tile - __ldg(tile_start + a)) * BIN_TILE;
-  hi = min(lo + BIN_TILE, __ldg(bin_start + a + 1));
-  return true;
-}
-
-static __global__ void __launch_bounds__(BIN_BLOCK)
-k_bin_hist(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ bin_start,
-           const uint32_t* __restrict__ tile_start, uint32_t n_bins, uint32_t bin_shift, uint32_t NB,
-           uint32_t* __restrict__ counts) {
-  extern __shared__ uint32_t bin_smem[];
-  const uint32_t bpb = 1u << bin_shift;
-  uint32_t bin, lo, hi;
-  if (!bin_tile_range(bin_start, tile_start, n_bins, blockIdx.x, bin, lo, hi)) return;
-  for (uint32_t b = threadIdx.x; b < bpb; b += BIN_BLOCK) bin_smem[b] = 0;
-  __syncthreads();
-  for (uint32_t p = lo + threadIdx.x; p < hi; p += BIN_BLOCK) atomicAdd(&bin_smem[__ldg(tmp_g + p) & (bpb - 1)], 1u);
-  __syncthreads();
-  for (uint32_t b = threadIdx.x; b < bpb; b += BIN_BLOCK) {
-    const uint32_t c = bin_smem[b], g = (bin << bin_shift) + b;
-    if (c && g < NB) atomicAdd(&counts[g], c);
-  }
-}
-
-// Placement with the tile sorted in shared memory first, so that the entries of one bucket leave as
-// one run of consecutive 4-byte stores (a 32-byte sector for the typical 8 entries per bucket and
-// tile) instead of 8 scattered ones: 4-byte scattered stores cost the L2 as much as atomics do.
-constexpr int PLACE_BLOCK = 1024;
-static __global__ void __launch_bounds__(PLACE_BLOCK)
-k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp_v,
-            const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ tile_start, uint32_t n_bins,
-            uint32_t bin_shift, uint32_t NB, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
-  extern __shared__ uint32_t bin_smem[];
-  const uint32_t bpb = 1u << bin_shift;
-  uint32_t* hist = bin_smem;            // [bpb] counts, then running ranks, then (global position - slot) of the bucket
-  uint32_t* off = hist + bpb;           // [bpb] first slot of the bucket inside the tile
-  uint32_t* stage_v = off + bpb;        // [BIN_TILE]
-  uint16_t* stage_b = reinterpret_cast<uint16_t*>(stage_v + BIN_TILE);  // [BIN_TILE] low bucket bits (bpb <= 2^13)
-  __shared__ uint32_t warp_sums[PLACE_BLOCK / 32];
-  uint32_t bin, lo, hi;
-  if (!bin_tile_range(bin_start, tile_start, n_bins, blockIdx.x, bin, lo, hi)) return;
-  for (uint32_t b = threadIdx.x; b < bpb; b += PLACE_BLOCK) hist[b] = 0;
-  __syncthreads();
-  for (uint32_t p = lo + threadIdx.x; p < hi; p += PLACE_BLOCK) atomicAdd(&hist[__ldg(tmp_g + p) & (bpb - 1)], 1u);
-  __syncthreads();
-  // exclusive scan of hist over the block: thread t owns buckets [t*ipt, (t+1)*ipt), ipt <= 8
-  const uint32_t ipt = (bpb + PLACE_BLOCK - 1) / PLACE_BLOCK;
-  const uint32_t b0 = threadIdx.x * ipt;
-  uint32_t sum = 0;
-  for (uint32_t q = 0; q < ipt; q++) sum += b0 + q < bpb ? hist[b0 + q] : 0;
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t x = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= (uint32_t)o) x += y;
-  }
-  if (lane == 31) warp_sums[wid] = x;
-  __syncthreads();
-  if (wid == 0) {
-    uint32_t v = warp_sums[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= (uint32_t)o) v += y;
-    }
-    warp_sums[lane] = v;
-  }
-  __syncthreads();
-  // the owner keeps (first global position - first slot) of its buckets in registers until the tile is
-  // staged: two shared arrays instead of three let two 1024-thread blocks share an SM
-  uint32_t run = (wid ? warp_sums[wid - 1] : 0) + x - sum;
-  uint32_t delta[8];
-#pragma unroll
-  for (uint32_t q = 0; q < 8; q++) {
-    const uint32_t b = b0 + q;
-    delta[q] = 0;
-    if (q < ipt && b < bpb) {
-      const uint32_t c = hist[b], g = (bin << bin_shift) + b;
-      off[b] = run;
-      delta[q] = ((c && g < NB) ? atomicAdd(&cursor[g], c) : 0u) - run;
-      run += c;
-      hist[b] = 0;
-    }
-  }
-  __syncthreads();
-  for (uint32_t p = lo + threadIdx.x; p < hi; p += PLACE_BLOCK) {
-    const uint32_t lb = __ldg(tmp_g + p) & (bpb - 1);
-    const uint32_t slot = off[lb] + atomicAdd(&hist[lb], 1u);
-    stage_v[slot] = __ldg(tmp_v + p);
-    stage_b[slot] = (uint16_t)lb;
-  }
-  __syncthreads();
-#pragma unroll
-  for (uint32_t q = 0; q < 8; q++)
-    if (q < ipt && b0 + q < bpb) hist[b0 + q] = delta[q];
-  __syncthreads();
-  for (uint32_t slot = threadIdx.x; slot < hi - lo; slot += PLACE_BLOCK) entries[hist[stage_b[slot]] + slot] = stage_v[slot];
-}
-inline size_t bin_place_smem(uint32_t bin_shift) { return ((size_t)2 << bin_shift) * 4 + (size_t)BIN_TILE * 6; }
 
 // ---------------------------------------------------------------------------------------------
 // 128-bit vector loads / stores of plain structs (sizeof multiple of 16, 16-byte aligned).
@@ -675,7 +120,8 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
              const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start,
              uint32_t NB, const uint32_t* __restrict__ E_ptr, uint32_t S, uint32_t n_slices,
              Xyzz<F>* __restrict__ bucket_acc, Xyzz<F>* __restrict__ partials, uint32_t carry_in,
-             uint32_t* __restrict__ cut_count, uint32_t* __restrict__ cut_list, uint32_t cut_cap) {
+             uint32_t* __restrict__ cut_count, uint32_t* __restrict__ cut_list, uint32_t cut_cap,
+             const uint32_t* __restrict__ plane_x, const uint32_t* __restrict__ plane_y) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t E = __ldg(E_ptr);  // = bucket_start[NB], number of non-zero digits
   if (t >= n_slices || (uint64_t)t * S >= E) return;
@@ -697,12 +143,27 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
   // entry pos starts, and the entry index one further ahead: the two dependent loads of the gather
   // are off the critical path of the IMAD chains.
   constexpr int WORDS = 2 * F::PACKED_WORDS;
-  // entries == nullptr: the points to add are bases[s .. e) themselves, already signed (the output of the
-  // affine halving rounds, bucket_affine.cuh)
-  const bool direct = entries == nullptr;
+  // plane_x != nullptr: the points to add are items s .. e of the x / y planes the affine halving rounds left
+  // (bucket_affine.cuh), already signed; `entries` and `bases` are not used
+  const bool direct = plane_x != nullptr;
+  auto fetch = [&](uint32_t idx, uint32_t* w) {
+    if (direct) {
+      const uint4* qx = reinterpret_cast<const uint4*>(plane_x + (size_t)idx * F::PACKED_WORDS);
+      const uint4* qy = reinterpret_cast<const uint4*>(plane_y + (size_t)idx * F::PACKED_WORDS);
+#pragma unroll
+      for (int j = 0; j < F::PACKED_WORDS / 4; j++) {
+        const uint4 a = __ldg(qx + j), b = __ldg(qy + j);
+        w[4 * j] = a.x; w[4 * j + 1] = a.y; w[4 * j + 2] = a.z; w[4 * j + 3] = a.w;
+        w[F::PACKED_WORDS + 4 * j] = b.x; w[F::PACKED_WORDS + 4 * j + 1] = b.y;
+        w[F::PACKED_WORDS + 4 * j + 2] = b.z; w[F::PACKED_WORDS + 4 * j + 3] = b.w;
+      }
+    } else {
+      load_base_words<F>(bases + idx, w);
+    }
+  };
   uint32_t nxt[WORDS];
   uint32_t ent = direct ? s : __ldg(entries + s);
-  load_base_words<F>(bases + (ent & 0x7fffffffu), nxt);
+  fetch(ent & 0x7fffffffu, nxt);
   uint32_t ent_ahead = s + 1 < e ? (direct ? s + 1 : __ldg(entries + s + 1)) : ent;
   for (uint32_t pos = s; pos < e; pos++) {
     if (pos == gend) {
@@ -720,7 +181,7 @@ k_accumulate(const PackedAffine<F>* __restrict__ bases, uint32_t line_stride,
     const bool negate = (ent >> 31) != 0;
     ent = ent_ahead;
     if (pos + 1 < e) {
-      load_base_words<F>(bases + (ent & 0x7fffffffu), nxt);
+      fetch(ent & 0x7fffffffu, nxt);
       if (pos + 2 < e) ent_ahead = direct ? pos + 2 : __ldg(entries + pos + 2);
     }
     if (finite) {

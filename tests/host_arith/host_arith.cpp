@@ -116,13 +116,16 @@ extern "C" int host_madd_chain(int curve, int impl, const void* pts, size_t m, s
 #undef CALL
 }
 
-// Affine halving rounds (csrc/bucket_affine.cuh), the per-thread device function run thread by thread:
+// Affine halving rounds (csrc/bucket_affine.cuh), the per-thread device functions run thread by thread:
 // `rounds` rounds over the sorted entry list, T emulated threads, batches of at most m_max items.
+// (The kernel shares one inversion per block through a shared-memory product tree; here every thread
+// inverts its own batch product -- the same value.)
 // bases: API-layout affine points; entries: index | sign << 31, grouped by bucket (off0[NB + 1]).
 // Returns the number of points left; out_pts (API affine layout) / out_off ([NB + 1]) describe them.
 template <class F>
 static long ba_rounds(const uint32_t* bases_api, size_t n_bases, const uint32_t* entries, const uint32_t* off0, uint32_t NB,
                       uint32_t rounds, uint32_t T, uint32_t m_max, uint32_t* out_pts, uint32_t* out_off) {
+  constexpr int N = F::N;
   std::vector<PackedAffine<F>> packed(n_bases);
   for (size_t i = 0; i < n_bases; i++) {
     const ApiAffine<F>* a = reinterpret_cast<const ApiAffine<F>*>(bases_api) + i;
@@ -130,28 +133,42 @@ static long ba_rounds(const uint32_t* bases_api, size_t n_bases, const uint32_t*
     F::api_to_packed(a->y, packed[i].y);
   }
   std::vector<uint32_t> off_in(off0, off0 + NB + 1), off_out(NB + 1);
-  std::vector<PackedAffine<F>> cur, nxt;
-  std::vector<uint32_t> sc_prefix((size_t)T * m_max * F::N), sc_idx((size_t)T * m_max);
+  std::vector<uint4> cx, cy, nx, ny;  // planes (16-byte aligned)
+  std::vector<uint4> sc_prefix((size_t)T * m_max * N / 4);
+  std::vector<uint32_t> sc_idx((size_t)T * m_max);
+  BaPoints<F> in{packed.data(), entries, nullptr, nullptr};
   for (uint32_t r = 0; r < rounds; r++) {
     off_out[0] = 0;
     for (uint32_t g = 0; g < NB; g++) off_out[g + 1] = off_out[g] + ((off_in[g + 1] - off_in[g] + 1) >> 1);
-    nxt.assign(off_out[NB] + 1, PackedAffine<F>{});
-    for (uint32_t t = 0; t < T; t++) {
-      if (r == 0)
-        ba_round_thread<F, true>(t, T, packed.data(), entries, off_in.data(), off_out.data(), NB, m_max, nxt.data(),
-                                 sc_prefix.data(), sc_idx.data());
-      else
-        ba_round_thread<F, false>(t, T, cur.data(), nullptr, off_in.data(), off_out.data(), NB, m_max, nxt.data(),
-                                  sc_prefix.data(), sc_idx.data());
+    const size_t cap = (size_t)off_out[NB] + 1;
+    nx.assign(cap * N / 4, uint4{0, 0, 0, 0});
+    ny.assign(cap * N / 4, uint4{0, 0, 0, 0});
+    BaPoints<F> out{nullptr, nullptr, reinterpret_cast<uint32_t*>(nx.data()), reinterpret_cast<uint32_t*>(ny.data())};
+    const BaGeom gm = ba_geom(T, off_out[NB]);
+    std::vector<BaWalk> wk(T);
+    for (auto& w : wk) w.ready = false;
+    uint32_t* pre = reinterpret_cast<uint32_t*>(sc_prefix.data());
+    for (uint32_t i0 = 0; i0 < gm.per; i0 += m_max) {
+      std::vector<typename F::Elem> prod(T);
+      for (uint32_t t = 0; t < T; t++)
+        prod[t] = r == 0 ? ba_forward<F, true>(t, gm, i0, m_max, in, off_in.data(), off_out.data(), NB, wk[t], pre, sc_idx.data())
+                         : ba_forward<F, false>(t, gm, i0, m_max, in, off_in.data(), off_out.data(), NB, wk[t], pre, sc_idx.data());
+      for (uint32_t t = 0; t < T; t++) {
+        const typename F::Elem inv = F::inv(prod[t]);
+        if (r == 0) ba_backward<F, true>(t, gm, i0, m_max, in, out, inv, pre, sc_idx.data());
+        else ba_backward<F, false>(t, gm, i0, m_max, in, out, inv, pre, sc_idx.data());
+      }
     }
-    cur.swap(nxt);
+    cx.swap(nx);
+    cy.swap(ny);
+    in = BaPoints<F>{nullptr, nullptr, reinterpret_cast<uint32_t*>(cx.data()), reinterpret_cast<uint32_t*>(cy.data())};
     off_in = off_out;
   }
   const uint32_t left = off_in[NB];
   for (uint32_t i = 0; i < left; i++) {
     ApiAffine<F>* o = reinterpret_cast<ApiAffine<F>*>(out_pts) + i;
-    F::to_api(F::unpack(cur[i].x), o->x);
-    F::to_api(F::unpack(cur[i].y), o->y);
+    F::to_api(F::unpack(in.x + (size_t)i * N), o->x);
+    F::to_api(F::unpack(in.y + (size_t)i * N), o->y);
   }
   for (uint32_t g = 0; g <= NB; g++) out_off[g] = off_in[g];
   return (long)left;

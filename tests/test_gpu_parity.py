@@ -454,8 +454,11 @@ def test_context_busy_under_a_real_race(engine, oracle):
 
     def long_call():
         inside.set()
-        for _ in range(6):
-            results.append(engine.multiple_multiexp(w, bases, sc, 1, 8, True))
+        while len(results) < 6:
+            try:
+                results.append(engine.multiple_multiexp(w, bases, sc, 1, 8, True))
+            except engine.CudaError as e:  # the other thread's call holds the context right now
+                (busy if e.name == "ContextAlreadyInUse" else other).append(e)
 
     a = threading.Thread(target=long_call)
     a.start()

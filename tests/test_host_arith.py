@@ -138,7 +138,7 @@ def test_long_madd_chains_keep_invariants(host, oracle, curve, impl):
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-@pytest.mark.parametrize("rounds,T,m_max", [(1, 7, 5), (3, 16, 64), (5, 3, 9), (9, 1, 1000)])
+@pytest.mark.parametrize("rounds,T,m_max", [(1, 32, 5), (3, 64, 64), (5, 64, 2), (9, 32, 1000), (2, 96, 1)])
 def test_affine_halving_rounds(host, oracle, curve, rounds, T, m_max):
     """csrc/bucket_affine.cuh, the device function of one thread run thread by thread on the host: after any
     number of halving rounds the points left in a bucket still sum to the bucket's signed entries.  Buckets:
