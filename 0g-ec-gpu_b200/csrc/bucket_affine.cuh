@@ -49,6 +49,17 @@ MSM_D uint32_t ba_find_bucket(const uint32_t* __restrict__ off, uint32_t NB, uin
   return lo;
 }
 
+// Pull the line(s) holding [p, p + bytes) into the L2 without occupying a register: the rounds stream through
+// tens of GB with one dependent load chain per item, and ncu showed the warps waiting on those loads
+// (long_scoreboard 3.8 warps per issue) rather than on the multiplier.
+MSM_D void ba_prefetch(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 constexpr int BA_BLOCK = 128;
 constexpr uint32_t BA_KIND_COPY = 0, BA_KIND_ADD = 1, BA_KIND_DBL = 2, BA_KIND_SPECIAL = 3;
 
@@ -103,16 +114,12 @@ template <class F, bool GATHER> MSM_D typename F::Elem ba_in_y(const BaPoints<F>
 }
 template <class F> MSM_D bool ba_is_zero(const typename F::Elem& e) { return F::template is_multiple_of_p<0, 2>(e); }
 template <class F> MSM_D void ba_out(const BaPoints<F>& out, uint32_t k, const typename F::Elem& x, const typename F::Elem& y) {
-  uint32_t wx[F::N], wy[F::N];
-  F::to_packed(x, wx);  // canonical words: an all-zero (x, y) is the identity and nothing else
-  F::to_packed(y, wy);
-  uint4* qx = reinterpret_cast<uint4*>(out.x + (size_t)k * F::N);
-  uint4* qy = reinterpret_cast<uint4*>(out.y + (size_t)k * F::N);
-#pragma unroll
-  for (int j = 0; j < F::N / 4; j++) {
-    qx[j] = make_uint4(wx[4 * j], wx[4 * j + 1], wx[4 * j + 2], wx[4 * j + 3]);
-    qy[j] = make_uint4(wy[4 * j], wy[4 * j + 1], wy[4 * j + 2], wy[4 * j + 3]);
-  }
+  // Planes hold the field's register form (lazy [0, 2p) values are not folded): the identity is written as
+  // all-zero words explicitly, and a finite point never has x = y = 0 mod p, so "all words zero" still means
+  // the identity and nothing else for every reader (the next round, k_accumulate's plane mode).
+  static_assert(F::PACKED_WORDS == F::N, "planes store the register limbs");
+  ba_store_elem<F>(out.x + (size_t)k * F::N, x);
+  ba_store_elem<F>(out.y + (size_t)k * F::N, y);
 }
 
 // Position of a thread in the bucket structure while it walks its outputs in increasing order.
@@ -143,6 +150,7 @@ MSM_D typename F::Elem ba_forward(uint32_t t, const BaGeom& gm, uint32_t i0, uin
   using E = typename F::Elem;
   constexpr int N = F::N;
   E prefix = F::one();
+  const uint32_t n_items = __ldg(off_in + NB);  // inputs of the round
   for (uint32_t ii = 0; ii < m; ii++) {
     if (i0 + ii >= gm.per) break;
     const uint64_t k64 = ba_item(gm, t, i0 + ii);
@@ -164,6 +172,9 @@ MSM_D typename F::Elem ba_forward(uint32_t t, const BaGeom& gm, uint32_t i0, uin
       wk.n_in = __ldg(off_in + wk.g + 1) - wk.istart;
     }
     const uint32_t j = k - wk.ostart, a = wk.istart + 2 * j;
+    // the next item of this lane is 32 outputs = about 64 inputs further on: pull its line into the L2 now
+    // (plane rounds: -7 %; requesting the gather round's random table rows the same way doubled its time)
+    if (!GATHER && a + 65 < n_items) ba_prefetch(in.x + (size_t)(a + 64) * N);
     uint32_t kind = BA_KIND_COPY;
     if (2 * j + 1 < wk.n_in) {
       const E xa = ba_in_x<F, GATHER>(in, a), xb = ba_in_x<F, GATHER>(in, a + 1);
@@ -208,6 +219,14 @@ MSM_D void ba_backward(uint32_t t, const BaGeom& gm, uint32_t i0, uint32_t m, co
     const uint32_t k = (uint32_t)k64;
     const uint32_t word = scratch_idx[(size_t)ii * gm.T + t];
     const uint32_t a = word & 0x3fffffffu, kind = word >> 30;
+    // the item this lane handles next (ii - 1) sits about 64 inputs back
+    if (ii && !GATHER) {
+      ba_prefetch(scratch_prefix + ((size_t)(ii - 1) * gm.T + t) * N);
+      if (a >= 64) {
+        ba_prefetch(in.x + (size_t)(a - 64) * N);
+        ba_prefetch(in.y + (size_t)(a - 64) * N);
+      }
+    }
     const E xa = ba_in_x<F, GATHER>(in, a), ya = ba_in_y<F, GATHER>(in, a);
     if (kind == BA_KIND_COPY) {
       ba_out<F>(out, k, xa, ya);

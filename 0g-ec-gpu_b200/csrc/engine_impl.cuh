@@ -176,8 +176,11 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
          2 * Arena::padded(n_lines * heavy_cap * 4) + Arena::padded(n_lines * chunk_cap * 4) +
          Arena::padded(n_lines * chunk_cap * sizeof(Xyzz<F>));
   }
-  // Affine halving rounds: worth it while a round still gives every resident thread a batch long enough to
-  // amortise its inversion (~380 products) and buckets still hold a few entries each.
+  // Affine halving rounds (bucket_affine.cuh).  MEASURED SLOWER than the XYZZ slice kernel on B200 (2^24 points:
+  // 32.6 ms against 30.5 ms of accumulation; per addition 189 ps in the gather round and 127 - 159 ps in the
+  // plane rounds against 150 ps for XYZZ; DESIGN.md section 3b, profiles/r02_affine_rounds.md), so they are OFF
+  // unless asked for: MSM_B200_BA=1 applies the heuristic below (rounds while every resident thread still gets
+  // a batch that amortises the block's inversion), MSM_B200_BA_ROUNDS=k forces k rounds.
   pl.ba_rounds = 0;
   if (ba_supported<F>() && n_lines == 1 && pl.E_max < (1ull << 30)) {
     uint32_t bps = F::N <= 8 ? 4 : 2;  // resident blocks per SM (launch bounds of k_affine_round)
@@ -190,11 +193,11 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     if (const char* env = getenv("MSM_B200_BA_BATCH")) pl.ba_batch = (uint32_t)std::max(16, atoi(env));
     uint32_t min_per_thread = 96;
     if (const char* env = getenv("MSM_B200_BA_MIN_BATCH")) min_per_thread = (uint32_t)std::max(1, atoi(env));
-    int force = -1;
-    if (const char* env = getenv("MSM_B200_BA_ROUNDS")) force = atoi(env);
+    int force = 0;
     if (const char* env = getenv("MSM_B200_BA")) {
-      if (atoi(env) == 0) force = 0;
+      if (atoi(env) != 0) force = -1;
     }
+    if (const char* env = getenv("MSM_B200_BA_ROUNDS")) force = atoi(env);
     uint64_t eb = pl.E_max / n_sub + g.W;  // entries of one sub-batch, upper bound
     uint32_t r = 0;
     while (r < 8) {
@@ -575,6 +578,30 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
   std::vector<Job> jobs;
   if (resident) {
     if (skip + n > resident->n) return MSM_ERR_INVALID;
+    {
+      // lazy window tables, as in multiple_multiexp (msm_b200.h, "Window tables by policy"): the second call
+      // over the same range builds the table of every shard the range covers completely
+      msm_bases* mb = const_cast<msm_bases*>(resident);
+      if (mb->shape_L == n && mb->shape_chunks == (uint32_t)skip) {
+        mb->shape_calls++;
+      } else {
+        mb->shape_L = n;
+        mb->shape_chunks = (uint32_t)skip;
+        mb->shape_calls = 1;
+        mb->table_failed = false;
+      }
+      if (mb->table_policy != MSM_TABLE_OFF && !mb->table_explicit && !mb->table_failed && mb->shape_calls >= 2 &&
+          !ctx->window_override && !getenv("MSM_B200_WINDOW")) {
+        for (auto& sh : mb->shards) {
+          if (sh.table || sh.n == 0 || sh.start < skip || sh.start + sh.n > skip + n) continue;
+          if (build_table_impl<F>(ctx, sh, 0, 0, /*budgeted=*/true) != MSM_OK) {
+            mb->table_failed = true;
+            cudaGetLastError();
+            break;
+          }
+        }
+      }
+    }
     for (const auto& sh : resident->shards) {
       const size_t lo = std::max(skip, sh.start), hi = std::min(skip + n, sh.start + sh.n);
       if (lo >= hi) continue;
@@ -609,7 +636,9 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
     shadow.curve = ctx->curve;
     shadow.window_override = ctx->window_override;
     shadow.abort_flag = ctx->abort_flag;
-    int rc = make_plan<F>(&shadow, (uint32_t)job.cnt, 1, 1, plans[j], job.table_c);
+    // host scalars of a large shard arrive in pipelined sub-batches, as in multiple_multiexp
+    const uint32_t n_sub = job.cnt >= (1u << 23) ? 8 : (job.cnt >= (1u << 20) ? 4 : 1);
+    int rc = make_plan<F>(&shadow, (uint32_t)job.cnt, 1, 1, plans[j], job.table_c, n_sub);
     if (rc) {
       rcs[j] = rc;
       return;
@@ -636,13 +665,28 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
       }
       d_bases = dp;
     }
-    e = cudaMemcpyAsync(ds, static_cast<const char*>(scalars) + job.s_off * 32, job.cnt * 32,
-                        cudaMemcpyHostToDevice, dc.stream);
-    if (e != cudaSuccess) return fail(e, "scalars H2D");
-    rc = enqueue_msm<F>(&shadow, dc, plans[j], d_bases, (uint32_t)job.cnt, ds, d_out, true);
+    const Plan& pl = plans[j];
+    const char* h_sc = static_cast<const char*>(scalars) + job.s_off * 32;
+    if (pl.n_sub > 1) {
+      cudaStreamWaitEvent(dc.copy_stream, dc.ev[0], 0);
+      const size_t L_sub = (pl.geo.L + pl.n_sub - 1) / pl.n_sub;
+      for (uint32_t sb = 0; sb < pl.n_sub && e == cudaSuccess; sb++) {
+        const size_t first = std::min((size_t)sb * L_sub, job.cnt), cnt = std::min(L_sub, job.cnt - first);
+        if (cnt) e = cudaMemcpyAsync(ds + first * 8, h_sc + first * 32, cnt * 32, cudaMemcpyHostToDevice, dc.copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(dc.ev_copy[sb], dc.copy_stream);
+      }
+    } else {
+      e = cudaMemcpyAsync(ds, h_sc, job.cnt * 32, cudaMemcpyHostToDevice, dc.stream);
+    }
+    if (e != cudaSuccess) {
+      cudaStreamSynchronize(dc.copy_stream);
+      return fail(e, "scalars H2D");
+    }
+    rc = enqueue_msm<F>(&shadow, dc, pl, d_bases, (uint32_t)job.cnt, ds, d_out, true, pl.n_sub > 1 ? dc.ev_copy : nullptr);
     if (rc) {
       rcs[j] = rc;
       errs[j] = shadow.err;
+      cudaStreamSynchronize(dc.copy_stream);
       cudaStreamSynchronize(dc.stream);
       return;
     }
@@ -658,8 +702,9 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
   }
   for (size_t j = 0; j < jobs.size(); j++) {
     if (rcs[j] != MSM_OK) {  // first error wins (ec-gpu-proxy/src/multiexp.rs:351-364)
-      for (auto& job : jobs) {
+      for (auto& job : jobs) {  // nothing may still read the caller's buffers when the call returns
         cudaSetDevice(ctx->devs[job.dev_idx].dev);
+        cudaStreamSynchronize(ctx->devs[job.dev_idx].copy_stream);
         cudaStreamSynchronize(ctx->devs[job.dev_idx].stream);
       }
       set_error(ctx, errs[j]);

@@ -437,6 +437,32 @@ def test_context_busy_and_errors(engine, oracle):
         kern2.multiexp(engine.Worker(), pts, oracle.gen_scalars(0, 1, 64), 0)
 
 
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("rounds", [1, 3, 6])
+def test_affine_halving_rounds_path(engine, oracle, ws, curve, rounds, monkeypatch):
+    """csrc/bucket_affine.cuh (batched-affine bucket accumulation; off by default because it measured slower,
+    profiles/r02_affine_rounds.md): forced on, results stay bit-exact -- random inputs with a window table, the
+    adversarial set (identity bases, P + P, P - P, equal scalars -> heavy buckets), host scalars in sub-batches."""
+    monkeypatch.setenv("MSM_B200_BA_ROUNDS", str(rounds))
+    monkeypatch.setenv("MSM_B200_BA_BATCH", "64")
+    n = 1 << 17
+    pts, sc = _synth(engine, ws[curve], curve, n)
+    want = oracle.multiexp_cpu(curve, pts, sc)
+    bases = engine.upload_multiexp_bases(ws[curve], pts)
+    for call in range(3):  # plain, plain, window table (built by policy on the second call)
+        got = engine.multiple_multiexp(ws[curve], bases, sc, 1, 8, True)
+        assert_same_points(oracle, curve, got, want, f"affine rounds, call {call}")
+    assert bases.table_window() != 0
+    bases.free()
+    apts, asc = adversarial_inputs(oracle, curve, 1 << 12)
+    # identity bases make the reference's CPU path error out; the oracle's batched form skips them like the engine
+    abases = engine.upload_multiexp_bases(ws[curve], apts)
+    for chunks in (1, 4):
+        got = engine.multiple_multiexp(ws[curve], abases, asc, chunks, 8, True)
+        assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, apts, asc, chunks), f"adversarial, {chunks} chunks")
+    abases.free()
+
+
 def test_context_busy_under_a_real_race(engine, oracle):
     """Two host threads on ONE workspace: while thread A is inside a long multiple_multiexp call, thread
     B's call on the same context must come back with CudaError::ContextAlreadyInUse (MSM_ERR_BUSY,
