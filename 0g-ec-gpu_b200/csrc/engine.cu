@@ -479,30 +479,12 @@ int msm_scalars_from_montgomery_device(msm_ctx* ctx, const void* d_in, size_t n,
 int msm_multiple_multiexp_montgomery(msm_ctx* ctx, const msm_bases* bases, const void* scalars_mont, size_t L,
                                      uint32_t num_chunks, void* out) {
   if (!ctx || !bases || !scalars_mont || !out || bases->ctx != ctx || L == 0 || L >= (1ull << 31)) return MSM_ERR_INVALID;
-  void* d_sc = nullptr;
-  size_t n_tasks = 0;
-  {
-    LOCK_OR_BUSY(ctx);
-    DeviceCtx& dc = ctx->devs[0];
-    CU_TRY(ctx, cudaSetDevice(dc.dev));
-    CU_TRY(ctx, cudaMalloc(&d_sc, L * 32));
-    cudaError_t e = cudaMemcpyAsync(d_sc, scalars_mont, L * 32, cudaMemcpyHostToDevice, dc.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(dc.stream);
-    if (e != cudaSuccess) {
-      cudaFree(d_sc);
-      set_error(ctx, std::string("msm_multiple_multiexp_montgomery: ") + cudaGetErrorString(e));
-      return MSM_ERR_CUDA;
-    }
-    n_tasks = (bases->n / L) * num_chunks;
-  }
-  int rc = msm_scalars_from_montgomery_device(ctx, d_sc, L, d_sc);
-  void* d_out = nullptr;
-  const size_t out_bytes = n_tasks * (ctx->ops->api_point_bytes / 2) * 3;
-  if (rc == MSM_OK && cudaMalloc(&d_out, out_bytes ? out_bytes : 1) != cudaSuccess) rc = MSM_ERR_CUDA;
-  if (rc == MSM_OK) rc = msm_multiple_multiexp_device(ctx, bases, d_sc, L, num_chunks, d_out);
-  if (rc == MSM_OK && cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = MSM_ERR_CUDA;
-  cudaFree(d_sc);
-  if (d_out) cudaFree(d_out);
+  LOCK_OR_BUSY(ctx);
+  // the conversion is fused into the digit decomposition (sort.cu: load_scalar_geo): same call path as
+  // msm_multiple_multiexp, pipelined upload included
+  ctx->scalars_mont = true;
+  const int rc = ctx->ops->multiple_multiexp(ctx, bases, scalars_mont, L, num_chunks, out, false);
+  ctx->scalars_mont = false;
   return rc;
 }
 

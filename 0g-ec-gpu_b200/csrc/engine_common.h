@@ -77,6 +77,7 @@ struct msm_ctx {
   std::string err;
   msm_timings tm{};
   uint32_t window_override = 0;
+  bool scalars_mont = false;  // set for the duration of a *_montgomery call: the scalar row is Fr in Montgomery form
   // 1 for the caller's handle + 1 per live msm_bases: msm_ctx_destroy only marks the context closed while
   // resident bases still point at it; the last msm_bases_free (or msm_ctx_destroy) tears it down
   std::atomic<int> refs{1};

@@ -91,6 +91,7 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   g.fold = table_c ? 1 : 0;
   g.table_stride = table_stride ? table_stride : L;
   g.point_offset = 0;
+  g.mont = ctx->scalars_mont ? (curve_is_bn254(ctx->curve) ? 1u : 2u) : 0u;
   if (n_lines != 1 || num_chunks != 1 || n_sub < 1) n_sub = 1;
   pl.n_sub = n_sub;
   g.num_chunks = num_chunks;
@@ -118,6 +119,15 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   uint32_t S = (uint32_t)(pl.E_max / n_sub / (148ull * 512 * 8));
   if (const char* env = getenv("MSM_B200_SLICE")) S = (uint32_t)atoi(env);
   S = S < 8 ? 8 : (S > 1024 ? 1024 : S);
+  {
+    // Few digits over few buckets (BLS12-381 shards of 2^19 points at c = 16: 256 digits per bucket, S = 13):
+    // every bucket was cut into ~20 slices and went through the one-warp-per-bucket fix-up, which is built for a
+    // FEW very heavy buckets -- 2.8 ms of a 6.7 ms call (profiles/r02_launches_bls_2p19.csv).  Slices of at least
+    // an eighth of the average bucket keep a bucket's partial slots within what one thread adds up serially.
+    const uint64_t avg_bucket = pl.E_max / n_sub / (g.NB ? g.NB : 1);
+    const uint32_t s_min = (uint32_t)(avg_bucket / 8 < 64 ? avg_bucket / 8 : 64);
+    if (S < s_min && !getenv("MSM_B200_SLICE")) S = s_min;
+  }
   pl.S = S;
   pl.n_slices = (uint32_t)((pl.E_max + S - 1) / S);
   pl.slices_cap = pl.n_slices / n_sub + g.W / S + 3;

@@ -328,6 +328,104 @@ template <class P> MSM_HD Fp<P> fp_mul2_nored(const Fp<P>& a, const Fp<P>& b, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dedicated squaring (the reference has none: FIELD_sqr = FIELD_mul(a, a), ag-build/cl/field.cl:313-315).
+//
+//   a^2 = sum_i a_i 2^(32 i) * V_i,   V_i = a_i 2^(32 i) + 2 * sum_{j>i} a_j 2^(32 j)
+//
+// so row i of the operand-scanning product above multiplies by a_i a vector V_i whose limbs below i are zero:
+// limb i is a_i, limb i+1 is d_(i+1) with bit 0 cleared, limb j > i+1 is d_j, where d = 2a (one funnel shift
+// per limb; a < 2p < 2^(32N-1), so d fits N limbs; bit 0 of d_(i+1) is the top bit of a_i, which belongs to
+// 2 a_i and not to the tail).  In the even/odd row form only the skipped products of the EVEN accumulator are
+// free: the odd accumulator's chain also carries the 64-bit shift of the row (madc_wide_cc3 reads [j+2]) and
+// the carry of the orphan limb, so a skipped product there still costs two carry adds -- the pipe time of the
+// IMAD.WIDE.X it replaces.  (Moving the orphan's carry elsewhere does not work: it has the weight of the low
+// limb of exactly that chain's first pair.)  Products executed: N^2 - sum_i ceil(i/2) = 48 of 64 for N = 8,
+// 108 of 144 for N = 12, plus the N^2 + N of the reduction, against 15 / 23 shift-and-mask instructions for d:
+// 6 - 8 % of a squaring's pipe time (measured: DESIGN.md section 3).  A full N(N+1)/2 squaring needs the
+// separated (product, then reduction) form, whose 2N-limb intermediate costs more carry adds on this chip,
+// where IADD3.X shares the multiplier's datapath, than the 12 / 30 further products it saves.
+// The doubled vector is below 4p, so a row adds less than 5p 2^32 to T: the accumulator invariant needs
+// 5p < 2^(32N) (true for BN254 Fq / Fr and BLS12-381 Fq; BLS12-381 Fr, p = 0.45 * 2^256, keeps the product).
+// ---------------------------------------------------------------------------------------------
+template <class P> MSM_HD constexpr bool fp_has_fast_sqr() { return P::P(P::N - 1) < 0x33333333u; }
+
+// Row I >= 1 of the squaring: mont_row<P, false> with v[j] = 0 for j < I.
+template <class P, int I>
+MSM_HD void mont_row_sq(uint32_t* E, uint32_t* O, const uint32_t* v, uint32_t bi) {
+  constexpr int N = P::N;
+  constexpr int JE = I + (I & 1);  // first even limb >= I
+  E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int j = 0; j < N - 2; j += 2) {
+    if (j + 1 < I) {  // product skipped: shift and carry only
+      O[j] = addc_cc(O[j + 2], 0u);
+      O[j + 1] = addc_cc(O[j + 3], 0u);
+    } else {
+      madc_wide_cc3(O[j], O[j + 1], v[j + 1], bi, O[j + 2], O[j + 3]);
+    }
+  }
+  madc_wide_0(O[N - 2], O[N - 1], v[N - 1], bi);
+  if (JE <= N - 2) {
+    mad_wide_cc(E[JE], E[JE + 1], v[JE], bi);
+#pragma unroll
+    for (int j = JE + 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], v[j], bi);
+    O[N - 1] = addc(O[N - 1], 0u);
+  }
+  const uint32_t m = mul_lo(E[0], P::INV);
+  mad_wide_cc(O[0], O[1], P::P(1), m);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(O[j], O[j + 1], P::P(j + 1), m);
+  mad_wide_cc(E[0], E[1], P::P(0), m);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], P::P(j), m);
+  O[N - 1] = addc(O[N - 1], 0u);
+}
+
+template <class P, int I> struct SqRows {
+  // rows I, I+1: (E, O) = (Y, X) then (X, Y), as in fp_mul_nored
+  static MSM_HD void run(uint32_t* X, uint32_t* Y, const uint32_t* a, const uint32_t* d) {
+    constexpr int N = P::N;
+    uint32_t v[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = j < I ? 0u : (j == I ? a[I] : (j == I + 1 ? (d[j] & ~1u) : d[j]));
+    mont_row_sq<P, I>(Y, X, v, a[I]);
+    if (I + 1 < N) {
+      uint32_t w[N];
+#pragma unroll
+      for (int j = 0; j < N; j++) w[j] = j < I + 1 ? 0u : (j == I + 1 ? a[I + 1] : (j == I + 2 ? (d[j] & ~1u) : d[j]));
+      mont_row_sq<P, I + 1>(X, Y, w, a[I + 1]);
+    }
+    SqRows<P, I + 2>::run(X, Y, a, d);
+  }
+};
+template <class P> struct SqRows<P, P::N + 1> {
+  static MSM_HD void run(uint32_t*, uint32_t*, const uint32_t*, const uint32_t*) {}
+};
+
+// a^2 / R without the final conditional subtraction; a < 2p; result < a^2/R + p (< 2p)
+template <class P> MSM_HD Fp<P> fp_sqr_nored(const Fp<P>& a) {
+  constexpr int N = P::N;
+  static_assert(N % 2 == 0, "even limb count required");
+  if (!fp_has_fast_sqr<P>()) return fp_mul_nored<P>(a, a);
+  uint32_t d[N];
+  d[0] = a.v[0] << 1;
+#pragma unroll
+  for (int j = 1; j < N; j++) d[j] = (a.v[j] << 1) | (a.v[j - 1] >> 31);
+  uint32_t X[N], Y[N], v0[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) v0[j] = j == 0 ? a.v[0] : (j == 1 ? (d[1] & ~1u) : d[j]);
+  mont_row<P, true>(X, Y, v0, a.v[0]);
+  SqRows<P, 1>::run(X, Y, a.v, d);
+  // last row had E = Y, O = X:  result = (E >> 32) + O
+  Fp<P> r;
+  r.v[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
+  r.v[N - 1] = addc(X[N - 1], 0u);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Carry-save variant of the same product.  On B200 the carry-in form IMAD.WIDE.U32.X holds the
 // multiplier pipe for twice as long as a carry-free IMAD.WIDE.U32 (tools/imad_peak.cu,
 // profiles/r01_imad_peak_v2.json), and a field product is ~100 of them.  Here NO multiply takes a
@@ -413,7 +511,11 @@ template <class P> MSM_HD Fp<P> fp_mul_cs(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
-template <class P> MSM_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
+template <class P> MSM_HD Fp<P> fp_sqr(const Fp<P>& a) {
+  Fp<P> r = fp_sqr_nored<P>(a);
+  fp_csub_p<P>(r.v);
+  return r;
+}
 
 // Montgomery <-> canonical
 template <class P> MSM_HD Fp<P> fp_to_mont(const Fp<P>& a) {
@@ -567,7 +669,7 @@ template <class P> struct FieldSatLazy {
     return z == 0 || e == 0;
   }
   static MSM_HD Elem mul(const Elem& a, const Elem& b) { return fp_mul_nored<P>(a, b); }
-  static MSM_HD Elem sqr(const Elem& a) { return fp_mul_nored<P>(a, a); }
+  static MSM_HD Elem sqr(const Elem& a) { return fp_sqr_nored<P>(a); }
   // a*b - c*d: (a*b + (2p - c)*d)/R < 8p^2/R + p < 4p -> one fold back below 2p
   static MSM_HD Elem mul_sub(const Elem& a, const Elem& b, const Elem& c, const Elem& d) {
     Elem r = fp_mul2_nored<P>(a, b, neg<2, 1>(c), d);

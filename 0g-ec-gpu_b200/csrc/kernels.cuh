@@ -218,7 +218,7 @@ template <class F> MSM_D Xyzz<F> block_sum_xyzz(Xyzz<F> v, Xyzz<F>* sh) {
 // visit: the bucket array is zero-filled (= infinity) before the first sub-batch.  Buckets spread
 // over more than HEAVY_SPAN slices (skewed scalars; the short top window of a folded table) go to
 // a second list that k_fixup_heavy reduces with one warp each.
-constexpr uint32_t HEAVY_SPAN = 16;
+constexpr uint32_t HEAVY_SPAN = 32;
 constexpr uint32_t HEAVY_CHUNK = 256;  // partial slots one warp sums in k_fixup_heavy
 // work lists of one line: [cut_count, heavy_count, chunk_count] then the arrays below
 struct FixupLists {

@@ -5,6 +5,29 @@
 
 namespace msm {
 
+// Scalar i as canonical little-endian words.  geo.mont != 0: the row holds Fr elements in Montgomery form and the
+// conversion PrimeFieldRepr::to_bigint does on the host (ag-types/src/impls.rs:7-18; FIELD_unmont,
+// ag-build/cl/field.cl:365-377) happens here, fused into every decomposition pass (one Fr product per read, no
+// extra pass over the row and no second copy of it).
+MSM_D void load_scalar_geo(const uint32_t* scalars, uint32_t i, const Geometry& geo, uint32_t k[8]) {
+  load_scalar(scalars, i, k);
+  if (geo.mont == 1) {
+    Fp<Bn254Fr> a;
+#pragma unroll
+    for (int j = 0; j < 8; j++) a.v[j] = k[j];
+    a = fp_from_mont<Bn254Fr>(a);
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = a.v[j];
+  } else if (geo.mont == 2) {
+    Fp<Bls381Fr> a;
+#pragma unroll
+    for (int j = 0; j < 8; j++) a.v[j] = k[j];
+    a = fp_from_mont<Bls381Fr>(a);
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = a.v[j];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Signed-digit decomposition.  k = sum_w d_w 2^(c w),  d_w in [-(2^(c-1) - 1), 2^(c-1)].
 // W*c >= scalar_bits + 1 guarantees no carry out of the top window (the reference's kernel drops
@@ -81,7 +104,7 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, Geometry geo,
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= geo.L) return;
   uint32_t k[8];
-  load_scalar(scalars, i, k);
+  load_scalar_geo(scalars, i, geo, k);
   const uint32_t task = i / geo.chunk_len;
   const uint32_t base = task * geo.W;
   auto body = [&](uint32_t w, uint32_t bucket, bool neg) {
@@ -224,34 +247,79 @@ static __global__ void k_scan_finish(uint32_t* __restrict__ out, uint32_t n, con
 // hb = g >> bin_shift; hb_region[hb] = bucket_start[hb << bin_shift] is where bin hb starts.
 // ---------------------------------------------------------------------------------------------
 constexpr int PART_BLOCK = 512;
+constexpr int PART_ITEMS = 2;  // scalars per thread when the window size is a template argument (tile = 1024)
+
+// The decomposition of for_each_digit_c into a register array: dg[w] = (bucket - 1) | negative << 31, or
+// 0xffffffff for a zero digit.  k_partition decomposes every scalar ONCE and keeps its digits in registers
+// between the histogram pass and the placement pass (it used to read and decompose the row twice).
+template <int C> MSM_D void decompose_c(const uint32_t k[8], uint32_t W, uint32_t* dg) {
+  constexpr uint32_t half = 1u << (C - 1);
+  constexpr uint32_t mask = (1u << C) - 1u;
+  constexpr int MAXW = (256 + C - 1) / C + 1;
+  uint32_t carry = 0;
+#pragma unroll
+  for (int w = 0; w < MAXW; w++) {
+    dg[w] = 0xffffffffu;
+    if ((uint32_t)w < W) {
+      const int bit = w * C, word = bit >> 5, sh = bit & 31;
+      const uint32_t lo = word < 8 ? k[word < 8 ? word : 0] : 0u;
+      const uint32_t hi = word + 1 < 8 ? k[word + 1 < 8 ? word + 1 : 0] : 0u;
+      const uint32_t raw = (__funnelshift_r(lo, hi, sh) & mask) + carry;
+      carry = raw > half;
+      if (raw != 0 && raw != (1u << C)) dg[w] = carry ? (((1u << C) - raw - 1u) | 0x80000000u) : (raw - 1u);
+    }
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(PART_BLOCK)
 k_partition(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t tile, uint32_t bin_shift, uint32_t n_bins,
             const uint32_t* __restrict__ region_start, uint32_t region_shift, uint32_t* __restrict__ bin_cursor,
-            uint32_t* __restrict__ tmp_g, uint32_t* __restrict__ tmp_v) {
+            uint2* __restrict__ tmp) {
   extern __shared__ uint32_t part_smem[];
   uint32_t* hist = part_smem;                 // [n_bins] counts, then running cursors
   uint32_t* off = hist + n_bins;              // [n_bins] exclusive offsets inside the block
   uint32_t* gbase = off + n_bins;             // [n_bins] global base of this block's run
-  uint32_t* stage_g = gbase + n_bins;         // [tile * W]
-  uint32_t* stage_v = stage_g + (size_t)tile * geo.W;
+  uint2* stage = reinterpret_cast<uint2*>(gbase + n_bins + (n_bins & 1));  // [tile * W] (bucket id, entry), 8-byte aligned
   __shared__ uint32_t total_sh;
   const uint32_t first = blockIdx.x * tile;
   for (uint32_t b = threadIdx.x; b < n_bins; b += PART_BLOCK) hist[b] = 0;
   __syncthreads();
+  constexpr int CC = C == 0 ? 8 : C;
+  constexpr int MAXW = (256 + CC - 1) / CC + 1;
+  uint32_t dg[C == 0 ? 1 : PART_ITEMS][C == 0 ? 1 : MAXW];
   // pass 1: histogram of high bins
-  for (uint32_t t = threadIdx.x; t < tile; t += PART_BLOCK) {
-    const uint32_t i = first + t;
-    if (i >= geo.L) break;
-    uint32_t k[8];
-    load_scalar(scalars, i, k);
-    const uint32_t base = (i / geo.chunk_len) * geo.W;
-    auto body = [&](uint32_t w, uint32_t bucket, bool) {
-      const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
-      atomicAdd(&hist[g >> bin_shift], 1u);
-    };
-    if (C == 0) for_each_digit(k, geo.c, geo.W, body);
-    else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
+  if (C == 0) {
+    for (uint32_t t = threadIdx.x; t < tile; t += PART_BLOCK) {
+      const uint32_t i = first + t;
+      if (i >= geo.L) break;
+      uint32_t k[8];
+      load_scalar_geo(scalars, i, geo, k);
+      const uint32_t base = (i / geo.chunk_len) * geo.W;
+      for_each_digit(k, geo.c, geo.W, [&](uint32_t w, uint32_t bucket, bool) {
+        const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+        atomicAdd(&hist[g >> bin_shift], 1u);
+      });
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < PART_ITEMS; it++) {
+      const uint32_t i = first + it * PART_BLOCK + threadIdx.x;
+#pragma unroll
+      for (int w = 0; w < MAXW; w++) dg[it][w] = 0xffffffffu;
+      if (it * PART_BLOCK + threadIdx.x < tile && i < geo.L) {
+        uint32_t k[8];
+        load_scalar_geo(scalars, i, geo, k);
+        decompose_c<CC>(k, geo.W, dg[it]);
+        const uint32_t gb = geo.fold ? task_of(i, geo) * geo.B : (i / geo.chunk_len) * geo.W * geo.B;
+#pragma unroll
+        for (int w = 0; w < MAXW; w++)
+          if (dg[it][w] != 0xffffffffu) {
+            const uint32_t g = gb + (geo.fold ? 0u : (uint32_t)w * geo.B) + (dg[it][w] & 0x7fffffffu);
+            atomicAdd(&hist[g >> bin_shift], 1u);
+          }
+      }
+    }
   }
   __syncthreads();
   // exclusive scan of the bins (n_bins <= 4 * PART_BLOCK), one global reservation per non-empty bin
@@ -278,43 +346,55 @@ k_partition(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t tile, u
     if (threadIdx.x == 0) total_sh = total;
   }
   __syncthreads();
-  // pass 2: same decomposition, place (g, entry) in the block-local bin order
-  for (uint32_t t = threadIdx.x; t < tile; t += PART_BLOCK) {
-    const uint32_t i = first + t;
-    if (i >= geo.L) break;
-    uint32_t k[8];
-    load_scalar(scalars, i, k);
-    const uint32_t base = (i / geo.chunk_len) * geo.W;
-    auto body = [&](uint32_t w, uint32_t bucket, bool neg) {
-      const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
-      const uint32_t hb = g >> bin_shift;
-      const uint32_t slot = off[hb] + atomicAdd(&hist[hb], 1u);
-      const uint32_t idx = geo.fold ? w * geo.table_stride + geo.point_offset + i : i;
-      stage_g[slot] = g;
-      stage_v[slot] = idx | (neg ? 0x80000000u : 0u);
-    };
-    if (C == 0) for_each_digit(k, geo.c, geo.W, body);
-    else for_each_digit_c<(C == 0 ? 8 : C)>(k, geo.W, body);
+  // pass 2: place (g, entry) in the block-local bin order
+  if (C == 0) {
+    for (uint32_t t = threadIdx.x; t < tile; t += PART_BLOCK) {
+      const uint32_t i = first + t;
+      if (i >= geo.L) break;
+      uint32_t k[8];
+      load_scalar_geo(scalars, i, geo, k);
+      const uint32_t base = (i / geo.chunk_len) * geo.W;
+      for_each_digit(k, geo.c, geo.W, [&](uint32_t w, uint32_t bucket, bool neg) {
+        const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
+        const uint32_t hb = g >> bin_shift;
+        const uint32_t slot = off[hb] + atomicAdd(&hist[hb], 1u);
+        const uint32_t idx = geo.fold ? w * geo.table_stride + geo.point_offset + i : i;
+        stage[slot] = make_uint2(g, idx | (neg ? 0x80000000u : 0u));
+      });
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < PART_ITEMS; it++) {
+      const uint32_t i = first + it * PART_BLOCK + threadIdx.x;
+      const uint32_t gb = geo.fold ? task_of(i, geo) * geo.B : (i / geo.chunk_len) * geo.W * geo.B;
+#pragma unroll
+      for (int w = 0; w < MAXW; w++)
+        if (dg[it][w] != 0xffffffffu) {
+          const uint32_t g = gb + (geo.fold ? 0u : (uint32_t)w * geo.B) + (dg[it][w] & 0x7fffffffu);
+          const uint32_t hb = g >> bin_shift;
+          const uint32_t slot = off[hb] + atomicAdd(&hist[hb], 1u);
+          const uint32_t idx = geo.fold ? (uint32_t)w * geo.table_stride + geo.point_offset + i : i;
+          stage[slot] = make_uint2(g, idx | (dg[it][w] & 0x80000000u));
+        }
+    }
   }
   __syncthreads();
-  // write every bin's run to its region: consecutive slots of one bin are consecutive in memory
+  // write every bin's run to its region: consecutive slots of one bin are consecutive 8-byte pairs in memory
   const uint32_t total = total_sh;
   for (uint32_t sidx = threadIdx.x; sidx < total; sidx += PART_BLOCK) {
-    const uint32_t g = stage_g[sidx];
-    const uint32_t hb = g >> bin_shift;
-    const uint32_t dst = gbase[hb] + (sidx - off[hb]);
-    tmp_g[dst] = g;
-    tmp_v[dst] = stage_v[sidx];
+    const uint2 pr = stage[sidx];
+    const uint32_t hb = pr.x >> bin_shift;
+    tmp[gbase[hb] + (sidx - off[hb])] = pr;
   }
 }
 
-static __global__ void k_final_scatter(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp_v,
+static __global__ void k_final_scatter(const uint2* __restrict__ tmp,
                                        const uint32_t* __restrict__ E_ptr, uint32_t* __restrict__ cursor,
                                        uint32_t* __restrict__ entries) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= __ldg(E_ptr)) return;
-  const uint32_t pos = atomicAdd(&cursor[__ldg(tmp_g + i)], 1u);
-  entries[pos] = __ldg(tmp_v + i);
+  const uint2 pr = __ldg(tmp + i);
+  entries[atomicAdd(&cursor[pr.x], 1u)] = pr.y;
 }
 
 template <int C> inline cudaError_t partition_set_smem(size_t bytes) {
@@ -323,14 +403,14 @@ template <int C> inline cudaError_t partition_set_smem(size_t bytes) {
 inline cudaError_t launch_partition(uint32_t grid, size_t smem, cudaStream_t st, const uint32_t* scalars,
                                     const Geometry& geo, uint32_t tile, uint32_t bin_shift, uint32_t n_bins,
                                     const uint32_t* region_start, uint32_t region_shift, uint32_t* bin_cursor,
-                                    uint32_t* tmp_g, uint32_t* tmp_v) {
+                                    uint2* tmp) {
   cudaError_t e = cudaSuccess;
 #define MSM_PART_CASE(CC)                                                                                        \
   case CC:                                                                                                       \
     e = partition_set_smem<CC>(smem);                                                                            \
     if (e == cudaSuccess)                                                                                        \
       k_partition<CC><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, region_start,       \
-                                                      region_shift, bin_cursor, tmp_g, tmp_v);                   \
+                                                      region_shift, bin_cursor, tmp);                            \
     break;
   switch (geo.c) {
     MSM_PART_CASE(16) MSM_PART_CASE(17) MSM_PART_CASE(18) MSM_PART_CASE(19) MSM_PART_CASE(20)
@@ -339,7 +419,7 @@ inline cudaError_t launch_partition(uint32_t grid, size_t smem, cudaStream_t st,
       e = partition_set_smem<0>(smem);
       if (e == cudaSuccess)
         k_partition<0><<<grid, PART_BLOCK, smem, st>>>(scalars, geo, tile, bin_shift, n_bins, region_start, region_shift,
-                                                       bin_cursor, tmp_g, tmp_v);
+                                                       bin_cursor, tmp);
   }
 #undef MSM_PART_CASE
   return e;
@@ -376,7 +456,7 @@ k_bin_count(const uint32_t* __restrict__ scalars, Geometry geo, uint32_t bin_shi
     const uint32_t i = first + t;
     if (i >= geo.L) break;
     uint32_t k[8];
-    load_scalar(scalars, i, k);
+    load_scalar_geo(scalars, i, geo, k);
     const uint32_t base = (i / geo.chunk_len) * geo.W;
     auto body = [&](uint32_t w, uint32_t bucket, bool) {
       const uint32_t g = geo.fold ? task_of(i, geo) * geo.B + (bucket - 1) : (base + w) * geo.B + (bucket - 1);
@@ -451,7 +531,7 @@ MSM_D bool bin_tile_range(const uint32_t* __restrict__ bin_start, const uint32_t
 }
 
 static __global__ void __launch_bounds__(BIN_BLOCK)
-k_bin_hist(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ bin_start,
+k_bin_hist(const uint2* __restrict__ tmp, const uint32_t* __restrict__ bin_start,
            const uint32_t* __restrict__ tile_start, uint32_t n_bins, uint32_t bin_shift, uint32_t NB,
            uint32_t* __restrict__ counts) {
   extern __shared__ uint32_t bin_smem[];
@@ -460,7 +540,7 @@ k_bin_hist(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ bin_
   if (!bin_tile_range(bin_start, tile_start, n_bins, blockIdx.x, bin, lo, hi)) return;
   for (uint32_t b = threadIdx.x; b < bpb; b += BIN_BLOCK) bin_smem[b] = 0;
   __syncthreads();
-  for (uint32_t p = lo + threadIdx.x; p < hi; p += BIN_BLOCK) atomicAdd(&bin_smem[__ldg(tmp_g + p) & (bpb - 1)], 1u);
+  for (uint32_t p = lo + threadIdx.x; p < hi; p += BIN_BLOCK) atomicAdd(&bin_smem[__ldg(&tmp[p].x) & (bpb - 1)], 1u);
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < bpb; b += BIN_BLOCK) {
     const uint32_t c = bin_smem[b], g = (bin << bin_shift) + b;
@@ -473,7 +553,7 @@ k_bin_hist(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ bin_
 // tile) instead of 8 scattered ones: 4-byte scattered stores cost the L2 as much as atomics do.
 constexpr int PLACE_BLOCK = 1024;
 static __global__ void __launch_bounds__(PLACE_BLOCK)
-k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp_v,
+k_bin_place(const uint2* __restrict__ tmp,
             const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ tile_start, uint32_t n_bins,
             uint32_t bin_shift, uint32_t NB, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
   extern __shared__ uint32_t bin_smem[];
@@ -487,7 +567,7 @@ k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp
   if (!bin_tile_range(bin_start, tile_start, n_bins, blockIdx.x, bin, lo, hi)) return;
   for (uint32_t b = threadIdx.x; b < bpb; b += PLACE_BLOCK) hist[b] = 0;
   __syncthreads();
-  for (uint32_t p = lo + threadIdx.x; p < hi; p += PLACE_BLOCK) atomicAdd(&hist[__ldg(tmp_g + p) & (bpb - 1)], 1u);
+  for (uint32_t p = lo + threadIdx.x; p < hi; p += PLACE_BLOCK) atomicAdd(&hist[__ldg(&tmp[p].x) & (bpb - 1)], 1u);
   __syncthreads();
   // exclusive scan of hist over the block: thread t owns buckets [t*ipt, (t+1)*ipt), ipt <= 8
   const uint32_t ipt = (bpb + PLACE_BLOCK - 1) / PLACE_BLOCK;
@@ -531,9 +611,10 @@ k_bin_place(const uint32_t* __restrict__ tmp_g, const uint32_t* __restrict__ tmp
   }
   __syncthreads();
   for (uint32_t p = lo + threadIdx.x; p < hi; p += PLACE_BLOCK) {
-    const uint32_t lb = __ldg(tmp_g + p) & (bpb - 1);
+    const uint2 pr = __ldg(tmp + p);
+    const uint32_t lb = pr.x & (bpb - 1);
     const uint32_t slot = off[lb] + atomicAdd(&hist[lb], 1u);
-    stage_v[slot] = __ldg(tmp_v + p);
+    stage_v[slot] = pr.y;
     stage_b[slot] = (uint16_t)lb;
   }
   __syncthreads();
@@ -583,8 +664,7 @@ int enqueue_sort_binned(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geome
     return MSM_OK;
   }
   const size_t cap = pl.E_max / pl.n_sub + sg.W;
-  uint32_t* tmp_g = dc.arena.take<uint32_t>(cap);
-  uint32_t* tmp_v = dc.arena.take<uint32_t>(cap);
+  uint2* tmp = dc.arena.take<uint2>(cap);  // (bucket id, entry) pairs grouped by bin
   uint32_t* bin_count = dc.arena.take<uint32_t>(1024);  // [bin_count | bin_cursor]: one memset
   uint32_t* bin_cursor = dc.arena.take<uint32_t>(1024);
   uint32_t* bin_start = dc.arena.take<uint32_t>(1025);
@@ -595,16 +675,16 @@ int enqueue_sort_binned(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geome
   launch_bin_count((sg.L + BIN_COUNT_SCALARS - 1) / BIN_COUNT_SCALARS, st, scalars, sg, bin_shift, n_bins, bin_count);
   k_bin_scan<<<1, SCAN_BLOCK, 0, st>>>(bin_count, n_bins, bin_start, tile_start);
   const uint32_t tile = partition_tile(sg.W);
-  const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * sg.W) * 4;
+  const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * sg.W) * 4 + 8;
   CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, scalars, sg, tile, bin_shift, n_bins, bin_start, 0u,
-                               bin_cursor, tmp_g, tmp_v));
+                               bin_cursor, tmp));
   const uint32_t max_tiles = (uint32_t)(E_max / BIN_TILE) + n_bins + 1;
-  k_bin_hist<<<max_tiles, BIN_BLOCK, (size_t)4 << bin_shift, st>>>(tmp_g, bin_start, tile_start, n_bins, bin_shift, sg.NB,
+  k_bin_hist<<<max_tiles, BIN_BLOCK, (size_t)4 << bin_shift, st>>>(tmp, bin_start, tile_start, n_bins, bin_shift, sg.NB,
                                                                   b.counts);
   enqueue_bucket_scan(st, sg, b);
   const size_t psmem = bin_place_smem(bin_shift);
   CU_TRY(ctx, cudaFuncSetAttribute(k_bin_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-  k_bin_place<<<max_tiles, PLACE_BLOCK, psmem, st>>>(tmp_g, tmp_v, bin_start, tile_start, n_bins, bin_shift, sg.NB, b.cursor,
+  k_bin_place<<<max_tiles, PLACE_BLOCK, psmem, st>>>(tmp, bin_start, tile_start, n_bins, bin_shift, sg.NB, b.cursor,
                                                     b.entries);
   pl.scatter_passes = 0;
   dc.launches += 5;
@@ -622,8 +702,7 @@ int enqueue_sort_partition(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Ge
   enqueue_bucket_scan(st, sg, b);
   if (!dg) return MSM_OK;
   const size_t cap = pl.E_max / pl.n_sub + sg.W;
-  uint32_t* tmp_g = dc.arena.take<uint32_t>(cap);
-  uint32_t* tmp_v = dc.arena.take<uint32_t>(cap);
+  uint2* tmp = dc.arena.take<uint2>(cap);  // (bucket id, entry) pairs grouped by bin
   uint32_t* bin_cursor = dc.arena.take<uint32_t>(4096);
   uint32_t bins = 16;
   while (bins < 1024 && (uint64_t)bins * (4u << 20) < E_max * 4) bins <<= 1;  // ~4 MB of entries per bin
@@ -634,11 +713,11 @@ int enqueue_sort_partition(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Ge
   const uint32_t bin_shift = nb_log > bins_log ? nb_log - bins_log : 0;
   const uint32_t n_bins = (uint32_t)(((uint64_t)sg.NB + (1ull << bin_shift) - 1) >> bin_shift);
   const uint32_t tile = partition_tile(sg.W);
-  const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * sg.W) * 4;
+  const size_t smem = ((size_t)3 * n_bins + (size_t)2 * tile * sg.W) * 4 + 8;
   CU_TRY(ctx, cudaMemsetAsync(bin_cursor, 0, (size_t)n_bins * 4, st));
   CU_TRY(ctx, launch_partition((sg.L + tile - 1) / tile, smem, st, scalars, sg, tile, bin_shift, n_bins, b.bucket_start,
-                               bin_shift, bin_cursor, tmp_g, tmp_v));
-  k_final_scatter<<<(uint32_t)((E_max + 255) / 256), 256, 0, st>>>(tmp_g, tmp_v, b.bucket_start + sg.NB, b.cursor, b.entries);
+                               bin_shift, bin_cursor, tmp));
+  k_final_scatter<<<(uint32_t)((E_max + 255) / 256), 256, 0, st>>>(tmp, b.bucket_start + sg.NB, b.cursor, b.entries);
   pl.scatter_passes = 0;
   dc.launches += 2;
   return MSM_OK;

@@ -18,6 +18,8 @@ struct Geometry {
   uint32_t fold;       // 1: bases are a window table T[w][i] = 2^(c w) P_i, all windows of a task share one bucket set
   uint32_t table_stride;  // points per window in the table (= points of the resident shard)
   uint32_t point_offset;  // folded sub-batches: index of this batch's first point in the table
+  uint32_t mont;          // scalars arrive in Montgomery form (arkworks' in-memory Fr) and are converted while they
+                          // are decomposed: 0 no (canonical), 1 BN254 Fr, 2 BLS12-381 Fr
 };
 MSM_HD uint32_t task_of(uint32_t i, const Geometry& geo) { return geo.num_chunks == 1 ? 0u : i / geo.chunk_len; }
 

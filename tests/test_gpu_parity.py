@@ -302,6 +302,27 @@ def test_montgomery_scalars_on_device(engine, oracle, pyref, ws, curve):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_montgomery_scalars_fused_into_every_sort(engine, oracle, ws, curve, monkeypatch):
+    """The Montgomery -> canonical conversion is fused into the digit decomposition (sort.cu: load_scalar_geo):
+    every sort that reads the row must convert -- single-level, binned (forced), and the pipelined sub-batch
+    upload of a 2^20 row, with and without the window table."""
+    n = 1 << 20
+    pts, sc = _synth(engine, ws[curve], curve, n)
+    mont = oracle.fr_op(curve, 0, sc)  # canonical -> Montgomery
+    want = oracle.multiexp_cpu(curve, pts, sc)
+    bases = engine.upload_multiexp_bases(ws[curve], pts)
+    for call in range(3):  # plain, plain, table
+        got = engine.multiple_multiexp_montgomery(ws[curve], bases, mont, 1)
+        assert ws[curve].timings()["sub_batches"] == 4
+        assert_same_points(oracle, curve, got, want, f"montgomery row, call {call}")
+    monkeypatch.setenv("MSM_B200_SORT", "binned")
+    small = 1 << 14
+    got = engine.multiple_multiexp_montgomery(ws[curve], bases, mont[:small], 8)
+    assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc[:small], 8), "binned sort, 64 lines x 8 chunks")
+    bases.free()
+
+
+@pytest.mark.parametrize("curve", CURVES)
 @pytest.mark.parametrize("c,chunks", [(13, 1), (16, 1), (9, 16), (20, 1)])
 def test_two_level_scatter_path(engine, oracle, ws, curve, c, chunks, monkeypatch):
     """The partition + final-scatter sort that large calls use, forced on a small adversarial
