@@ -132,9 +132,9 @@ int scalar_fft_impl(msm_ctx* ctx, void* data, uint32_t log_n, const void* omega_
     dc.launches += 2;
   }
   const uint32_t R = log_n < 10 ? log_n : 10;
-  CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_first<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10));
+  CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_first<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 << 10));
   CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_pass<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10));
-  k_ntt_first<PR><<<(uint32_t)(n >> R), NTT_BLOCK, (size_t)32 << R, st>>>(d_x, d_y, log_n, R, d_tw);
+  k_ntt_first<PR><<<(uint32_t)(n >> R), NTT_BLOCK, (size_t)48 << R, st>>>(d_x, d_y, log_n, R, d_tw);  // 2^R elements + 2^(R-1) twiddles
   dc.launches += 1;
   for (uint32_t s0 = R; s0 < log_n;) {
     if (aborted(ctx)) {  // SingleFftKernel polls maybe_abort once per pass (ec-gpu-proxy/src/fft.rs:86-90)

@@ -98,6 +98,31 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   g.chunk_len = L / num_chunks;  // tail dropped, as ag-build/cl/multiexp.cl:235
   g.L = g.chunk_len * num_chunks;
   g.scalar_bits = scalar_bits(ctx->curve);
+  {
+    // Sub-batch boundaries.  Host scalars arrive back to back on the copy stream; sub-batch k can start when its
+    // last byte has landed and sub-batch k-1 is done.  With sizes growing by a factor q the first (small) upload
+    // is all that is exposed as long as q stays below the upload : compute speed ratio (~3.4 on one B200 with
+    // its own PCIe link; q = 2 leaves room for several GPUs pulling from one host).  MSM_B200_PIPELINE_RATIO=1
+    // gives equal sizes.
+    double q = 2.0;
+    if (const char* env = getenv("MSM_B200_PIPELINE_RATIO")) q = atof(env);
+    if (q < 1.0) q = 1.0;
+    double total = 0, w = 1;
+    for (uint32_t k = 0; k < n_sub; k++, w *= q) total += w;
+    double acc = 0;
+    w = 1;
+    pl.sub_first[0] = 0;
+    pl.sub_max = 0;
+    for (uint32_t k = 0; k < n_sub; k++, w *= q) {
+      acc += w;
+      uint32_t end = k + 1 == n_sub ? g.L : (uint32_t)((double)g.L * (acc / total));
+      if (end < pl.sub_first[k]) end = pl.sub_first[k];
+      if (end > g.L) end = g.L;
+      pl.sub_first[k + 1] = end;
+      pl.sub_max = std::max(pl.sub_max, end - pl.sub_first[k]);
+    }
+    for (uint32_t k = n_sub + 1; k < 9; k++) pl.sub_first[k] = g.L;
+  }
   uint32_t c = ctx->window_override;
   if (const char* env = getenv("MSM_B200_WINDOW")) {
     if (!c) c = (uint32_t)atoi(env);
@@ -116,7 +141,8 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   pl.E_max = (uint64_t)g.L * g.W;
   if (pl.E_max >= (1ull << 31) || (uint64_t)L * n_lines >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
   // slice length: enough slices to fill the machine several times over, few cut buckets
-  uint32_t S = (uint32_t)(pl.E_max / n_sub / (148ull * 512 * 8));
+  const uint64_t E_sub = (uint64_t)pl.sub_max * g.W;  // digits of the longest sub-batch
+  uint32_t S = (uint32_t)(E_sub / (148ull * 512 * 8));
   if (const char* env = getenv("MSM_B200_SLICE")) S = (uint32_t)atoi(env);
   S = S < 8 ? 8 : (S > 1024 ? 1024 : S);
   {
@@ -124,13 +150,13 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     // every bucket was cut into ~20 slices and went through the one-warp-per-bucket fix-up, which is built for a
     // FEW very heavy buckets -- 2.8 ms of a 6.7 ms call (profiles/r02_launches_bls_2p19.csv).  Slices of at least
     // an eighth of the average bucket keep a bucket's partial slots within what one thread adds up serially.
-    const uint64_t avg_bucket = pl.E_max / n_sub / (g.NB ? g.NB : 1);
+    const uint64_t avg_bucket = E_sub / (g.NB ? g.NB : 1);
     const uint32_t s_min = (uint32_t)(avg_bucket / 8 < 64 ? avg_bucket / 8 : 64);
     if (S < s_min && !getenv("MSM_B200_SLICE")) S = s_min;
   }
   pl.S = S;
   pl.n_slices = (uint32_t)((pl.E_max + S - 1) / S);
-  pl.slices_cap = pl.n_slices / n_sub + g.W / S + 3;
+  pl.slices_cap = (uint32_t)((E_sub + S - 1) / S) + g.W / S + 3;
   // buckets per reduction thread: the per-thread fix-up (first_weight * plain sum, a ~c-bit
   // double-and-add) is amortised over Q buckets; keep about one wave of threads on the machine
   {
@@ -152,7 +178,7 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   // sizes are upper bounds for every sub-batch (n_sub == 1: the whole call)
   b += Arena::padded((size_t)(g.NB + 1) * 4) * 3;                            // counts, bucket_start, cursor
   b += Arena::padded((size_t)(n_tiles + 1) * 4);                             // tile sums + grand total
-  b += Arena::padded((pl.E_max / n_sub + g.W) * 4);                          // entries
+  b += Arena::padded((E_sub + g.W) * 4);                                     // entries
   // measured slower than the bucket-range passes on B200 (2^24, c = 22: 6.8 vs 5.2 ms): off unless asked for
   pl.partition = false;
   if (const char* env = getenv("MSM_B200_PARTITION")) pl.partition = atoi(env) != 0;
@@ -164,15 +190,15 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     while ((1ull << nb_log) < g.NB) nb_log++;
     const uint32_t shift = nb_log > 10 ? (nb_log - 10 < 11 ? 11 : nb_log - 10) : 11;
     const bool fits = shift <= 13 && (((uint64_t)g.NB + (1ull << shift) - 1) >> shift) <= 1024;
-    bool want = pl.E_max / n_sub >= (1ull << 22);  // measured break-even against the single-level sort: ~2^21 digits
+    bool want = E_sub >= (1ull << 22);  // measured break-even against the single-level sort: ~2^21 digits
     if (const char* env = getenv("MSM_B200_SORT")) want = strcmp(env, "binned") == 0;
     if (want && fits && !pl.partition) {
       pl.sort_mode = 2;
       pl.bin_shift = shift;
     }
   }
-  if (pl.sort_mode == 2) b += 2 * Arena::padded((pl.E_max / n_sub + g.W) * 4) + 4 * Arena::padded(1025 * 4);
-  if (pl.partition) b += (2 * Arena::padded((pl.E_max / n_sub + g.W) * 4) + Arena::padded(4096 * 4));  // tmp_g, tmp_v, bin cursors
+  if (pl.sort_mode == 2) b += 2 * Arena::padded((E_sub + g.W) * 4) + 4 * Arena::padded(1025 * 4);
+  if (pl.partition) b += (2 * Arena::padded((E_sub + g.W) * 4) + Arena::padded(4096 * 4));  // (bucket, entry) pairs, bin cursors
   b += Arena::padded((size_t)g.NB * n_lines * sizeof(Xyzz<F>));              // bucket accumulators (shared by the sub-batches)
   b += Arena::padded((size_t)2 * pl.slices_cap * n_lines * sizeof(Xyzz<F>));  // slice partials
   b += 2 * Arena::padded((size_t)pl.n_tasks * pl.W_sets * pl.PG * sizeof(Xyzz<F>));  // group partials (ping-pong)
@@ -208,7 +234,7 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
       if (atoi(env) != 0) force = -1;
     }
     if (const char* env = getenv("MSM_B200_BA_ROUNDS")) force = atoi(env);
-    uint64_t eb = pl.E_max / n_sub + g.W;  // entries of one sub-batch, upper bound
+    uint64_t eb = E_sub + g.W;  // entries of one sub-batch, upper bound
     uint32_t r = 0;
     while (r < 8) {
       const bool want = force >= 0 ? (int)r < force
@@ -256,16 +282,15 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
   Xyzz<F>* group_partials2 = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
 
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
-  const uint32_t L_sub = (g.L + n_sub - 1) / n_sub;
   const size_t arena_mark = dc.arena.off;
   for (uint32_t sb = 0; sb < n_sub; sb++) {
     dc.arena.off = arena_mark;  // sub-batches are stream-ordered: they reuse the same scratch
     Geometry sg = g;
     uint32_t S = pl.S, n_slices = pl.n_slices;
     uint64_t E_max = pl.E_max;
-    const uint32_t first = sb * L_sub;
+    const uint32_t first = pl.sub_first[sb];
     if (n_sub > 1) {
-      sg.L = first < g.L ? (g.L - first < L_sub ? g.L - first : L_sub) : 0;
+      sg.L = pl.sub_first[sb + 1] - first;
       sg.chunk_len = sg.L ? sg.L : 1;
       sg.point_offset = g.fold ? first : 0;
       E_max = (uint64_t)sg.L * g.W;
@@ -276,7 +301,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     uint32_t* bucket_start = dc.arena.take<uint32_t>(g.NB + 1);
     uint32_t* cursor = dc.arena.take<uint32_t>(g.NB + 1);
     uint32_t* tile_sums = dc.arena.take<uint32_t>(n_tiles + 1);
-    uint32_t* entries = dc.arena.take<uint32_t>(pl.E_max / n_sub + g.W);
+    uint32_t* entries = dc.arena.take<uint32_t>((size_t)pl.sub_max * g.W + g.W);
     Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * pl.slices_cap * pl.n_lines);
     FixupLists fl;
     fl.n_lines = pl.n_lines;
@@ -488,7 +513,10 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   // previous chunk is already being sorted and accumulated (the 32 B/scalar upload is ~20 % of the
   // call otherwise).
   uint32_t n_sub = 1;
-  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 20)) n_sub = L >= (1u << 23) ? 8 : 4;
+  // measured with equal sizes (tools/e2e_timing.py, one B200): 2^20 .. 2^22 scalars are fastest in 2 sub-batches
+  // (6.26 ms against 6.44 unpipelined and 6.62 in 4 at 2^21), 2^24 in 8; with sizes growing by a factor of two
+  // (make_plan) four sub-batches expose the same first upload as fifteen equal ones
+  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 20)) n_sub = L >= (1u << 23) ? 4 : 2;
   if (const char* env = getenv("MSM_B200_PIPELINE")) {
     const int v = atoi(env);
     // MSM_B200_PIPELINE_DEVICE: also split device-resident rows (measurement of the split's own cost)
@@ -526,10 +554,8 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
       CU_TRY(ctx, cudaStreamWaitEvent(dc.copy_stream, dc.ev[0], 0));
       drain.a = dc.copy_stream;
       drain.b = dc.stream;
-      const size_t L_sub = (pl.geo.L + pl.n_sub - 1) / pl.n_sub;
       for (uint32_t sb = 0; sb < pl.n_sub; sb++) {
-        const size_t first = std::min((size_t)sb * L_sub, (size_t)L);
-        const size_t cnt = std::min(L_sub, (size_t)L - first);
+        const size_t first = pl.sub_first[sb], cnt = pl.sub_first[sb + 1] - first;
         if (cnt)
           CU_TRY(ctx, cudaMemcpyAsync(ds + first * 8, static_cast<const char*>(scalars) + first * 32, cnt * 32,
                                       cudaMemcpyHostToDevice, dc.copy_stream));
@@ -647,7 +673,7 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
     shadow.window_override = ctx->window_override;
     shadow.abort_flag = ctx->abort_flag;
     // host scalars of a large shard arrive in pipelined sub-batches, as in multiple_multiexp
-    const uint32_t n_sub = job.cnt >= (1u << 23) ? 8 : (job.cnt >= (1u << 20) ? 4 : 1);
+    const uint32_t n_sub = job.cnt >= (1u << 23) ? 4 : (job.cnt >= (1u << 20) ? 2 : 1);
     int rc = make_plan<F>(&shadow, (uint32_t)job.cnt, 1, 1, plans[j], job.table_c, n_sub);
     if (rc) {
       rcs[j] = rc;
@@ -679,9 +705,8 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
     const char* h_sc = static_cast<const char*>(scalars) + job.s_off * 32;
     if (pl.n_sub > 1) {
       cudaStreamWaitEvent(dc.copy_stream, dc.ev[0], 0);
-      const size_t L_sub = (pl.geo.L + pl.n_sub - 1) / pl.n_sub;
       for (uint32_t sb = 0; sb < pl.n_sub && e == cudaSuccess; sb++) {
-        const size_t first = std::min((size_t)sb * L_sub, job.cnt), cnt = std::min(L_sub, job.cnt - first);
+        const size_t first = pl.sub_first[sb], cnt = pl.sub_first[sb + 1] - first;
         if (cnt) e = cudaMemcpyAsync(ds + first * 8, h_sc + first * 32, cnt * 32, cudaMemcpyHostToDevice, dc.copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(dc.ev_copy[sb], dc.copy_stream);
       }

@@ -65,6 +65,10 @@ k_ntt_first(const uint32_t* __restrict__ x, uint32_t* __restrict__ y, uint32_t l
   extern __shared__ uint4 ntt_smem[];
   Fp<PR>* u = reinterpret_cast<Fp<PR>*>(ntt_smem);
   const uint32_t chunk = 1u << R, base = blockIdx.x << R;
+  // the 2^(R-1) twiddles these rounds use, omega^(k n / 2^R), staged once per block: round s reads
+  // tws[j << (R-1-s)] from shared memory instead of one scattered 32-byte global load per butterfly
+  Fp<PR>* tws = u + chunk;
+  for (uint32_t k = threadIdx.x; k < chunk / 2; k += NTT_BLOCK) tws[k] = ntt_ld<PR>(tw, (size_t)k << (log_n - R));
   for (uint32_t i = threadIdx.x; i < chunk; i += NTT_BLOCK) u[i] = ntt_ld<PR>(x, __brev(base + i) >> (32 - log_n));
   __syncthreads();
   for (uint32_t s = 0; s < R; s++) {
@@ -72,7 +76,9 @@ k_ntt_first(const uint32_t* __restrict__ x, uint32_t* __restrict__ y, uint32_t l
     for (uint32_t b = threadIdx.x; b < chunk / 2; b += NTT_BLOCK) {
       const uint32_t j = b & (m - 1), i0 = ((b - j) << 1) + j, i1 = i0 + m;
       Fp<PR> lo = u[i0], hi = u[i1];
-      ntt_butterfly<PR>(lo, hi, tw, (size_t)j << (log_n - s - 1));
+      const Fp<PR> t = j ? fp_mul<PR>(hi, tws[j << (R - 1 - s)]) : hi;
+      hi = fp_sub<PR>(lo, t);
+      lo = fp_add<PR>(lo, t);
       u[i0] = lo;
       u[i1] = hi;
     }

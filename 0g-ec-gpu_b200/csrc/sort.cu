@@ -663,7 +663,7 @@ int enqueue_sort_binned(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geome
     enqueue_bucket_scan(st, sg, b);
     return MSM_OK;
   }
-  const size_t cap = pl.E_max / pl.n_sub + sg.W;
+  const size_t cap = (size_t)pl.sub_max * sg.W + sg.W;
   uint2* tmp = dc.arena.take<uint2>(cap);  // (bucket id, entry) pairs grouped by bin
   uint32_t* bin_count = dc.arena.take<uint32_t>(1024);  // [bin_count | bin_cursor]: one memset
   uint32_t* bin_cursor = dc.arena.take<uint32_t>(1024);
@@ -701,7 +701,7 @@ int enqueue_sort_partition(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Ge
   if (dg) launch_digits<false>(dg, db, st, scalars, sg, b.counts, nullptr, 0u, sg.NB);
   enqueue_bucket_scan(st, sg, b);
   if (!dg) return MSM_OK;
-  const size_t cap = pl.E_max / pl.n_sub + sg.W;
+  const size_t cap = (size_t)pl.sub_max * sg.W + sg.W;
   uint2* tmp = dc.arena.take<uint2>(cap);  // (bucket id, entry) pairs grouped by bin
   uint32_t* bin_cursor = dc.arena.take<uint32_t>(4096);
   uint32_t bins = 16;

@@ -34,6 +34,8 @@ struct Plan {
   uint32_t slices_cap;  // upper bound of the slices of one sub-batch
   uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
   uint32_t n_sub;   // sub-batches of a pipelined single-task call (they continue one shared bucket array)
+  uint32_t sub_first[9];  // sub-batch k covers scalars [sub_first[k], sub_first[k+1]); sizes grow geometrically
+  uint32_t sub_max;       // longest sub-batch
   mutable uint32_t scatter_passes = 1;  // filled in by enqueue_msm (0: two-level partition scatter)
   bool partition;   // two-level scatter through a (bucket id, entry) temporary, global cursor atomics (measured slower)
   uint32_t sort_mode;  // 0: single-level atomic sort, 2: binned sort (shared-memory atomics)

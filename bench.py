@@ -457,13 +457,14 @@ def main():
         peaks, peak_src = measured_peaks()
         binned = t_last["scatter_passes"] == 0
         if binned:
-            # binned sort: scalars read by k_bin_count and twice by k_partition; (bucket, entry) pairs written
-            # once and read by k_bin_hist (bucket ids) and k_bin_place (both); sorted entries written once
-            sort_bytes = n_local * 32 * 3 + n_local * t_last["num_windows"] * (8 + 4 + 8 + 4)
+            # binned sort: scalars read by k_bin_count and once by k_partition (digits stay in registers between its
+            # two passes); 8-byte (bucket, entry) pairs written once and read by k_bin_hist (bucket ids: 4 B) and
+            # k_bin_place (8 B); sorted entries written once
+            sort_bytes = n_local * 32 * 2 + n_local * t_last["num_windows"] * (8 + 4 + 8 + 4)
             kernels = "k_bin_count + k_partition + k_bin_hist + scan + k_bin_place"
-            note = ("32 B/scalar read by 3 passes + per digit: 8 B written and 12 B read of the partitioned "
+            note = ("32 B/scalar read by 2 passes + per digit: 8 B written and 12 B read of the partitioned "
                     "(bucket, entry) pairs + 4 B of the sorted entry; all per-digit atomics are in shared memory, "
-                    "the phase is bound by shared-memory atomics and 4-byte store transactions, not by HBM bandwidth")
+                    "the phase is bound by shared-memory atomics and store transactions, not by HBM bandwidth")
         else:
             sort_bytes = n_local * 32 * (1 + t_last["scatter_passes"]) + n_local * t_last["num_windows"] * 4
             kernels = "k_digits<count> + scan + k_digits<scatter> x passes"
