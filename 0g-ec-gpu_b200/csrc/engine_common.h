@@ -154,5 +154,7 @@ const FieldOps* field_ops_bn254_lazy();
 const FieldOps* field_ops_bls381_lazy();
 const FieldOps* field_ops_bn254_g2();
 const FieldOps* field_ops_bls381_g2();
+void fill_field_ops_aux_bn254_g2(FieldOps& o);   // inst_bn254_g2_aux.cu
+void fill_field_ops_aux_bls381_g2(FieldOps& o);  // inst_bls381_g2_aux.cu
 
 }  // namespace msm

@@ -1036,8 +1036,9 @@ int ec_fft_impl(msm_ctx* ctx, void* jac, uint32_t log_n, const void* omegas_mont
   return MSM_OK;
 }
 
-template <class F> FieldOps make_field_ops(const char* name) {
-  FieldOps o;
+// The entry points of one field class in two halves, so that the slow-to-compile Fq2 instantiations can be split
+// over two translation units (inst_*_g2.cu: the MSM path; inst_*_g2_aux.cu: EC-FFT, helpers, test kernels).
+template <class F> void fill_field_ops_msm(FieldOps& o, const char* name) {
   o.name = name;
   o.api_point_bytes = sizeof(ApiAffine<F>);
   o.packed_point_bytes = sizeof(PackedAffine<F>);
@@ -1045,12 +1046,19 @@ template <class F> FieldOps make_field_ops(const char* name) {
   o.multiexp = &multiexp_impl<F>;
   o.convert_bases = &convert_bases_impl<F>;
   o.build_table = [](msm_ctx* c, msm_bases::Shard& sh, uint32_t w, size_t cl) { return build_table_impl<F>(c, sh, w, cl, false); };
+}
+template <class F> void fill_field_ops_aux(FieldOps& o) {
   o.synth_points = &synth_points_impl<F>;
   o.test_fq = &test_fq_impl<F>;
   o.test_ec = &test_ec_impl<F>;
   o.to_affine = &to_affine_impl<F>;
   o.sum_points = &sum_points_impl<F>;
   o.ec_fft = &ec_fft_impl<F>;
+}
+template <class F> FieldOps make_field_ops(const char* name) {
+  FieldOps o;
+  fill_field_ops_msm<F>(o, name);
+  fill_field_ops_aux<F>(o);
   return o;
 }
 

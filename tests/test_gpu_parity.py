@@ -484,6 +484,33 @@ def test_affine_halving_rounds_path(engine, oracle, ws, curve, rounds, monkeypat
     abases.free()
 
 
+@pytest.mark.parametrize("window,neg", [(8, 0), (8, 1), (5, 1)])
+def test_reference_cuda_kernel_equals_engine(engine, oracle, ws, window, neg, tmp_path):
+    """The reference's OWN kernel (ag-build/cl/multiexp.cl instantiated for BN254 as SourceBuilder does, compiled
+    for sm_100a by oracle/build_ref.py --cuda, launched with the geometry of ag-cuda-ec/src/multiexp.rs:27-72) run on
+    this GPU against the engine: 2 lines x 16 chunks, equal as group elements -- the parity notion of the reference's
+    test_multiexp_batch (ag-cuda-ec/src/multiexp.rs:93-145) with the reference kernel itself as the other side."""
+    import os
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_kernel_bn254")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_kernel_bn254 not built (needs /root/reference at build time)")
+    curve, L, lines, chunks = 0, 1 << 13, 2, 16
+    pts, sc = _synth(engine, ws[curve], curve, L * lines)
+    sc = sc[:L]
+    fb, fe, fo = (str(tmp_path / x) for x in ("bases.bin", "exps.bin", "out.bin"))
+    pts.tofile(fb)
+    sc.tofile(fe)
+    subprocess.run([exe, fb, fe, str(L), str(chunks), str(window), str(neg), "1", fo], check=True, capture_output=True)
+    ref = np.fromfile(fo, dtype=np.uint8).reshape(-1, 3 * FQ[curve])
+    bases = engine.upload_multiexp_bases(ws[curve], pts)
+    got = engine.multiple_multiexp(ws[curve], bases, sc, chunks, window, bool(neg))
+    bases.free()
+    assert ref.shape == got.shape == (lines * chunks, 96)
+    assert_same_points(oracle, curve, got, ref, f"engine vs reference kernel, window {window}, neg {neg}")
+
+
 def test_context_busy_under_a_real_race(engine, oracle):
     """Two host threads on ONE workspace: while thread A is inside a long multiple_multiexp call, thread
     B's call on the same context must come back with CudaError::ContextAlreadyInUse (MSM_ERR_BUSY,
