@@ -200,7 +200,12 @@ int msm_multiexp_resident(msm_ctx* ctx, const msm_bases* bases, size_t skip, con
  * {x, y, z} Montgomery (Vec<Curve>), infinity <=> z == 0; omegas_mont[i] = omega^(2^i) in arkworks'
  * in-memory Fr layout (4 x u64 little-endian, Montgomery form), n_omegas >= log_n entries (the
  * reference passes 32, ag-cuda-ec/src/ec_fft.rs:120-124).  Passing the powers of omega^-1 gives
- * the unscaled inverse transform (ag-cuda-ec/benches/ec_fft.rs:88-106).  Synchronous. */
+ * the unscaled inverse transform (ag-cuda-ec/benches/ec_fft.rs:88-106).  Synchronous.
+ * Precondition on G1: the twiddle multiplications use the GLV endomorphism (k P = k1 P + k2 phi(P)), which equals
+ * k P only for P in the prime-order subgroup.  BN254 G1 has cofactor 1 (every curve point qualifies); BLS12-381 G1 has
+ * a cofactor, so inputs must be subgroup points -- what arkworks' checked deserialisation and every KZG / AMT setup
+ * guarantee.  For on-curve points outside the subgroup set MSM_B200_ECFFT_GLV=0 (plain double-and-add, the
+ * reference's POINT_mul semantics for any point, about 1.8x slower).  G2 never uses the split. */
 int msm_ec_fft(msm_ctx* ctx, void* jacobian_inout, uint32_t log_n, const void* omegas_mont, uint32_t n_omegas);
 /* Same with the point array in device memory of device 0 (omegas stay a host array). */
 int msm_ec_fft_device(msm_ctx* ctx, void* d_jacobian_inout, uint32_t log_n, const void* omegas_mont,
