@@ -72,7 +72,9 @@ pub fn init_local_workspace() {
     LOCAL.with(|l| l.borrow_mut().get_or_insert_with(CudaWorkspace::new));
 }
 
-/// DeviceData (ag-cuda-proxy/src/params.rs:173-218): resident bases, freed on drop.
+/// DeviceData (ag-cuda-proxy/src/params.rs:173-218): resident bases, freed on drop.  The handle keeps its
+/// context alive (msm_b200.h, "Lifetime"): dropping it after its workspace -- a thread-local workspace that died
+/// before a `DeviceData` sent to another thread -- is safe.
 pub struct DeviceData(*mut sys::msm_bases);
 unsafe impl Send for DeviceData {}
 impl DeviceData {
@@ -88,6 +90,15 @@ impl Drop for DeviceData {
 
 pub mod multiexp {
     use super::*;
+
+    // Window tables need no call here: the second `multiple_multiexp_*` call with the same
+    // `(exponents.len(), num_chunks)` on one `DeviceData` builds the table that shape wants (msm_b200.h, "Window
+    // tables by policy").  The two functions below only override that policy.
+
+    /// Engine extension: 0 = never build a table behind the caller's back, 1 = lazily (default), 2 = now.
+    pub fn set_table_policy_st(bases_gpu: &DeviceData, policy: i32) -> CudaResult<()> {
+        check(GLOBAL.0, unsafe { sys::msm_bases_set_table_policy(GLOBAL.0, bases_gpu.0, policy) })
+    }
 
     /// Engine extension: window table for calls whose tasks have `chunk_len` points each (the
     /// per-segment commitment and AMT shapes, ag-cuda-ec/benches/{multiexp,amt}.rs).  Results are unchanged.

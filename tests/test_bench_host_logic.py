@@ -42,3 +42,33 @@ def test_bench_two_rank_control_flow_on_gloo():
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("OK [") == 1, r.stdout[-2000:]
+
+
+def test_golden_check_accepts_the_golden_and_rejects_anything_else():
+    """bench.golden_check: the bytes msm_to_affine returns for the golden point(s) compare equal, any flipped bit or a
+    missing row does not, unknown sizes give None (no claim)."""
+    import json
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+
+    g = json.load(open(os.path.join(HERE, "golden", "fullsize.json")))
+
+    def affine_bytes(rows):
+        xy = b"".join(bytes.fromhex(r["x"])[::-1] + bytes.fromhex(r["y"])[::-1] for r in rows)
+        return np.frombuffer(xy + bytes(r["inf"] for r in rows), dtype=np.uint8).copy()
+
+    one = affine_bytes([g["bn254_2p24"]["result"]])
+    assert bench.golden_check(0, 24, False, one, 32) == (True, "bn254_2p24")
+    bad = one.copy()
+    bad[5] ^= 1
+    assert bench.golden_check(0, 24, False, bad, 32)[0] is False
+    assert bench.golden_check(0, 24, False, one[:-1], 32)[0] is False
+    assert bench.golden_check(0, 19, False, one, 32) == (None, None)
+    bls = affine_bytes([g["bls12_381_2p22"]["result"]])
+    assert bench.golden_check(1, 22, False, bls, 48) == (True, "bls12_381_2p22")
+    rows = g["bn254_batched_1024x4096"]["results"]
+    assert bench.golden_check(0, 22, True, affine_bytes(rows), 32) == (True, "bn254_batched_1024x4096")
+    assert bench.golden_check(0, 22, True, affine_bytes(rows[::-1]), 32)[0] is False

@@ -282,3 +282,23 @@ def test_fft_oracle_vs_reference_cl_live(oracle, pyref, curve):
         jac[:, :2 * FQ[curve]] = oracle.gen_points(curve, 700 + log_n, n)
         jac[:, 2 * FQ[curve]:] = oracle.constant(curve, 1)
         assert_same_points(oracle, curve, ref_cl.ec_fft(curve, jac, oms), oracle.ec_fft(curve, jac, oms[0]), f"ec_fft 2^{log_n}")
+
+
+def test_fullsize_golden_file_is_the_oracle(oracle):
+    """tests/golden/fullsize.json (what the GPU tests and bench.py compare full-size results with) is the oracle's
+    output: the 2^20 entry is recomputed here (a few seconds); the larger entries come from the same script
+    (tests/golden/make_fullsize.py) and nest the same input stream."""
+    import json
+
+    g = json.load(open(os.path.join(HERE, "golden", "fullsize.json")))
+    n = 1 << 20
+    assert g["seed"] == 0x0BADC0DE and g["bn254_2p20"]["n"] == n
+    pts, sc = oracle.gen_points(0, g["seed"], n), oracle.gen_scalars(0, g["seed"], n)
+    xy, inf = oracle.to_affine(0, oracle.multiexp_cpu(0, pts, sc))
+    got = {"x": bytes(xy[0, :32][::-1]).hex(), "y": bytes(xy[0, 32:][::-1]).hex(), "inf": int(inf[0])}
+    assert got == g["bn254_2p20"]["result"]
+    # a chunk of the batched golden: task 7 of 1024 x 4096 is the MSM of points / scalars [7 * 4096, 8 * 4096)
+    lo, hi = 7 * 4096, 8 * 4096
+    xy, inf = oracle.to_affine(0, oracle.multiexp_cpu(0, pts[lo:hi], sc[lo:hi]))
+    want = g["bn254_batched_1024x4096"]["results"][7]
+    assert {"x": bytes(xy[0, :32][::-1]).hex(), "y": bytes(xy[0, 32:][::-1]).hex(), "inf": int(inf[0])} == want
