@@ -25,7 +25,8 @@ namespace msm {
 // cost of one bucket in the reduction, in field products (measured): with very many (task, window)
 // groups one thread owns a whole group and pays the two additions of the running sum; with few
 // groups the per-thread fix-up, the shared-memory tree and low occupancy triple that
-inline double reduce_cost_per_bucket(double n_groups) { return n_groups >= 32768.0 ? 34.0 : 90.0; }
+// (round 2, job r2_run13: 1024 .. 20480 groups reduce a bucket in 0.56 - 0.73 ns = 37 - 49 products' worth of time)
+inline double reduce_cost_per_bucket(double n_groups) { return n_groups >= 32768.0 ? 34.0 : (n_groups >= 512.0 ? 40.0 : 90.0); }
 
 inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_tasks_lines, size_t xyzz_bytes,
                               double* cost_out = nullptr) {

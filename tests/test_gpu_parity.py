@@ -595,6 +595,23 @@ def test_abort_mid_call_with_registered_scalars(engine, oracle):
     w.close()
 
 
+def test_too_many_lines_is_an_error_not_a_launch_failure(engine, oracle):
+    """n_lines = bases / exponents is unbounded in the reference API; the bucket kernels carry the line in gridDim.y
+    (<= 65535): beyond that the call reports MSM_ERR_TOO_LARGE instead of an opaque launch failure, and the context
+    stays usable."""
+    w = engine.Workspace(0)
+    period = oracle.gen_points(0, 3, 64)
+    pts = period[np.arange(65536) % 64].copy()
+    bases = engine.upload_multiexp_bases(w, pts)
+    with pytest.raises(engine.CudaError):
+        engine.multiple_multiexp(w, bases, oracle.gen_scalars(0, 3, 1), 1, 8, True)  # 65536 lines of one point
+    sc = oracle.gen_scalars(0, 4, 2)
+    got = engine.multiple_multiexp(w, bases, sc, 1, 8, True)                           # 32768 lines: fine
+    assert_same_points(oracle, 0, got, oracle.multiple_multiexp(0, pts, sc, 1), "32768 lines x 2 points")
+    bases.free()
+    w.close()
+
+
 def test_bases_outlive_their_workspace(engine, oracle):
     """Drop order: a DeviceData may be freed after its workspace was closed (msm_b200.h, "Lifetime")."""
     lib = engine.load_library()
