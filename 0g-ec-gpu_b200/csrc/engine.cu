@@ -133,7 +133,7 @@ int scalar_fft_impl(msm_ctx* ctx, void* data, uint32_t log_n, const void* omega_
   }
   const uint32_t R = log_n < 10 ? log_n : 10;
   CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_first<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 << 10));
-  CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_pass<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10));
+  CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_pass<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10));
   k_ntt_first<PR><<<(uint32_t)(n >> R), NTT_BLOCK, (size_t)48 << R, st>>>(d_x, d_y, log_n, R, d_tw);  // 2^R elements + 2^(R-1) twiddles
   dc.launches += 1;
   for (uint32_t s0 = R; s0 < log_n;) {
@@ -142,7 +142,7 @@ int scalar_fft_impl(msm_ctx* ctx, void* data, uint32_t log_n, const void* omega_
       return MSM_ERR_ABORTED;
     }
     const uint32_t r = log_n - s0 < 5 ? log_n - s0 : 5;
-    k_ntt_pass<PR><<<(uint32_t)(n >> (5 + r)), NTT_BLOCK, (size_t)1024 << r, st>>>(d_y, log_n, s0, r, d_tw);
+    k_ntt_pass<PR><<<(uint32_t)(n >> (5 + r)), NTT_BLOCK, ((size_t)1024 << r) + (((size_t)1 << r) - 1) * 1024, st>>>(d_y, log_n, s0, r, d_tw);  // tile + its twiddles
     dc.launches += 1;
     s0 += r;
   }

@@ -98,16 +98,28 @@ k_ntt_pass(uint32_t* __restrict__ y, uint32_t log_n, uint32_t s0, uint32_t r, co
   const uint32_t lo0 = (blockIdx.x & (tiles_lo - 1)) << 5;
   const size_t base = ((size_t)(blockIdx.x >> (s0 - 5)) << (s0 + r)) + lo0;
   const uint32_t elems = 32u << r;
+  // Twiddles of the tile, staged once: round t needs omega^(j << (log_n - s0 - t - 1)) for j = (qlow << s0) + lo0 + l,
+  // qlow < 2^t, l < 32 -- (2^r - 1) * 32 values per tile.  Reading them from the global table inside every butterfly
+  // left the warps waiting on those loads (ncu: long_scoreboard 5 - 6.6 per issue, multiplier pipe 60 % busy); staged
+  // together with the tile the latency is paid once per block.
+  Fp<PR>* tws = u + elems;
+  const uint32_t n_tw = ((1u << r) - 1) * 32;
+  for (uint32_t idx = threadIdx.x; idx < n_tw; idx += NTT_BLOCK) {
+    const uint32_t grp = (idx >> 5) + 1, l = idx & 31;
+    const uint32_t t = 31 - __clz(grp), qlow = grp - (1u << t);
+    const size_t j = ((size_t)qlow << s0) + lo0 + l;
+    tws[idx] = ntt_ld<PR>(tw, j << (log_n - s0 - t - 1));
+  }
   for (uint32_t e = threadIdx.x; e < elems; e += NTT_BLOCK) u[e] = ntt_ld<PR>(y, base + ((size_t)(e >> 5) << s0) + (e & 31));
   __syncthreads();
   for (uint32_t t = 0; t < r; t++) {
-    const uint32_t s = s0 + t;
     for (uint32_t b = threadIdx.x; b < elems / 2; b += NTT_BLOCK) {
       const uint32_t l = b & 31, qb = b >> 5;
       const uint32_t qlow = qb & ((1u << t) - 1), q0 = ((qb - qlow) << 1) + qlow, q1 = q0 + (1u << t);
-      const size_t j = ((size_t)qlow << s0) + lo0 + l;  // index mod 2^s
       Fp<PR> lo = u[q0 * 32 + l], hi = u[q1 * 32 + l];
-      ntt_butterfly<PR>(lo, hi, tw, j << (log_n - s - 1));
+      const Fp<PR> tm = (qlow | lo0 | l) ? fp_mul<PR>(hi, tws[(((1u << t) - 1 + qlow) << 5) + l]) : hi;  // j = 0: omega^0
+      hi = fp_sub<PR>(lo, tm);
+      lo = fp_add<PR>(lo, tm);
       u[q0 * 32 + l] = lo;
       u[q1 * 32 + l] = hi;
     }
