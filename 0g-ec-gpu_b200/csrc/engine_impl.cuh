@@ -171,7 +171,8 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     pl.Q = Q < 1 ? 1 : Q;
     // (A block tree carrying (sum_k (k+1) S, sum S, sum_j j P_j) instead of the per-thread first_weight x sum fix-up was
     // built and measured in round 2: 2.95 ms against 1.53 ms at 2^21 buckets -- the tree's partially filled warps cost
-    // more issue slots than the fix-ups they replace.)
+    // more issue slots than the fix-ups they replace.  An even split over exactly two blocks per SM instead of the
+    // power-of-two Q -- 1024 warps on 592 schedulers -- changed nothing either: 1.58 ms, job r2_run17.)
   }
   const uint32_t TG = g.B / pl.Q;
   pl.RW = TG < 128 ? TG : 128;
