@@ -150,8 +150,10 @@ template <class F> MSM_HD void xyzz_madd(Xyzz<F>& acc, const Affine<F>& b) {
   acc.zzz = F::mul(acc.zzz, ppp);                     // v<1.06
 }
 
-// a + b, add-2008-s: 12M + 2S
-template <class F> MSM_COLD Xyzz<F> xyzz_add(const Xyzz<F>& a, const Xyzz<F>& b) {
+// a + b, add-2008-s: 12M + 2S.  xyzz_add_inl is the body, inlined where the addition IS the hot loop (the running sums
+// of k_bucket_reduce: two additions per bucket; as an out-of-line call every operand goes through local memory);
+// xyzz_add is the one out-of-line copy per curve everything else calls.
+template <class F> MSM_HD Xyzz<F> xyzz_add_inl(const Xyzz<F>& a, const Xyzz<F>& b) {
   using E = typename F::Elem;
   if (xyzz_is_inf<F>(a)) return b;
   if (xyzz_is_inf<F>(b)) return a;
@@ -177,6 +179,7 @@ template <class F> MSM_COLD Xyzz<F> xyzz_add(const Xyzz<F>& a, const Xyzz<F>& b)
   o.zzz = F::mul(F::mul(a.zzz, b.zzz), ppp);
   return o;
 }
+template <class F> MSM_COLD Xyzz<F> xyzz_add(const Xyzz<F>& a, const Xyzz<F>& b) { return xyzz_add_inl<F>(a, b); }
 
 // XYZZ -> Jacobian with Z = ZZZ:  X' = X*ZZ^2, Y' = Y*ZZZ^2, Z' = ZZZ
 // (x = X'/Z'^2 = X ZZ^2 / ZZ^3 = X/ZZ;  y = Y'/Z'^3 = Y ZZZ^2 / ZZZ^3 = Y/ZZZ), written in the

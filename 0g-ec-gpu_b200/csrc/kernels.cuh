@@ -360,8 +360,8 @@ k_bucket_reduce(const Xyzz<F>* __restrict__ bucket_acc, uint32_t n_threads, uint
     const uint32_t b0 = (uint32_t)(f % B);  // weight of bucket f+k is b0 + k + 1
     Xyzz<F> run = xyzz_inf<F>();
     for (int k = (int)Q - 1; k >= 0; k--) {
-      run = xyzz_add<F>(run, load_vec(&bucket_acc[f + k]));
-      res = xyzz_add<F>(res, run);
+      run = xyzz_add_inl<F>(run, load_vec(&bucket_acc[f + k]));
+      res = xyzz_add_inl<F>(res, run);
     }
     if (b0) res = xyzz_add<F>(res, xyzz_mul_small<F>(run, b0));
   }
