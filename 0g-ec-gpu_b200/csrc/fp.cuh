@@ -634,6 +634,9 @@ template <class P> struct FieldSatLazy {
     fp_csub_kp<P, 2>(r.v);
     return r;
   }
+  // (Round 2 tried the correction as one asm block with a predicated add chain and the limbs of 2p as immediates --
+  // 2N + 2 instructions instead of 3N + 1: BN254 unchanged (29.36 against 29.41 ms of accumulation at 2^24),
+  // BLS12-381 4.5 % slower (19.66 against 18.82 ms at 2^22): the block is a scheduling barrier for ptxas.  Job r2_run18.)
   template <int K, int LM> static MSM_HD Elem sub(const Elem& a, const Elem& b) {
     Elem r;
     r.v[0] = sub_cc(a.v[0], b.v[0]);
