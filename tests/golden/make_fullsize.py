@@ -12,6 +12,8 @@ ec-gpu-proxy/tests/multiexp.rs:99 (`into_affine()` on both sides):
   bn254_batched_1024x4096                  configs[4]: 1024 MSMs of 2^12 points (ag-cuda-ec/benches/multiexp.rs:19-22,56)
   bn254_amt_10x2p21_2048                   10 lines x 2^21 points, 2048 chunks (ag-cuda-ec/benches/amt.rs:18-55):
                                            SHA-256 of all 20480 results + the first 8 of them
+  bls12_381_batched_256x4096               256 BLS12-381 MSMs of 2^12 points (SHA-256 + the first 8 results)
+  bn254_g2_2p20, bls12_381_g2_2p18         G2 over Fq2: one MSM each
 
 Usage:  python tests/golden/make_fullsize.py [--only NAME ...]      (about ten minutes on 8 cores)
 The output, tests/golden/fullsize.json, is committed; the GPU tests and bench.py compare against it.
@@ -103,6 +105,27 @@ def main():
         doc["bn254_amt_10x2p21_2048"] = {"curve": 0, "lines": lines, "L": L, "num_chunks": chunks,
                                          "sha256": affine_digest(0, r), "first_results": affine_hex(0, r[:8])}
         print("bn254 AMT shape: %.1f s" % (time.time() - t0), flush=True)
+
+    if want("bls12_381_batched_256x4096"):
+        t0 = time.time()
+        L, chunks = 1 << 20, 256
+        pts = O.gen_points(1, SEED, L)
+        sc = O.gen_scalars(1, SEED, L)
+        r = O.multiple_multiexp(1, pts, sc, chunks)
+        doc["bls12_381_batched_256x4096"] = {"curve": 1, "L": L, "num_chunks": chunks, "sha256": affine_digest(1, r),
+                                             "first_results": affine_hex(1, r[:8])}
+        print("bls12-381 batched: %.1f s" % (time.time() - t0), flush=True)
+
+    for name, curve, k in (("bn254_g2_2p20", 2, 20), ("bls12_381_g2_2p18", 3, 18)):
+        if want(name):
+            t0 = time.time()
+            n = 1 << k
+            pts = O.gen_points(curve, SEED, n)
+            sc = O.gen_scalars(curve, SEED, n)
+            r = O.multiexp_cpu(curve, pts, sc)
+            doc[name] = {"curve": curve, "n": n, "result": affine_hex(curve, r)[0],
+                         "oracle_seconds": round(time.time() - t0, 2), "host_threads": O.ncores()}
+            print("%s: %.1f s" % (name, time.time() - t0), flush=True)
 
     with open(OUT, "w") as f:
         json.dump(doc, f, indent=0, sort_keys=True)

@@ -160,3 +160,29 @@ def test_amt_shape_bit_exact(engine, oracle, golden):
             assert _digest(oracle, 0, got) == g["sha256"], path
     finally:
         s.close()
+
+
+def test_bls381_batched_256x4096_bit_exact(engine, oracle, golden):
+    """The batched shape of configs[4] on the other curve: 256 BLS12-381 MSMs of 2^12 points."""
+    g = golden["bls12_381_batched_256x4096"]
+    s = _Synth(engine, oracle, 1, g["L"], g["L"])
+    try:
+        for path, got in _run_paths(engine, s, g["num_chunks"]).items():
+            assert got.shape[0] == g["num_chunks"]
+            assert _hex_points(oracle, 1, got[:8]) == g["first_results"], path
+            assert _digest(oracle, 1, got) == g["sha256"], path
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("name,curve", [("bn254_g2_2p20", 2), ("bls12_381_g2_2p18", 3)])
+def test_g2_fullsize_bit_exact(engine, oracle, golden, name, curve):
+    """G2 over Fq2 at 2^20 / 2^18 points: same paths, same parity notion."""
+    g = golden[name]
+    assert g["curve"] == curve
+    s = _Synth(engine, oracle, curve, g["n"], g["n"])
+    try:
+        for path, got in _run_paths(engine, s, 1).items():
+            assert _hex_points(oracle, curve, got)[0] == g["result"], path
+    finally:
+        s.close()

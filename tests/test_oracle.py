@@ -302,3 +302,29 @@ def test_fullsize_golden_file_is_the_oracle(oracle):
     xy, inf = oracle.to_affine(0, oracle.multiexp_cpu(0, pts[lo:hi], sc[lo:hi]))
     want = g["bn254_batched_1024x4096"]["results"][7]
     assert {"x": bytes(xy[0, :32][::-1]).hex(), "y": bytes(xy[0, 32:][::-1]).hex(), "inf": int(inf[0])} == want
+
+
+@pytest.mark.parametrize("name,curve", [("bn254_g2_2p20", 2), ("bls12_381_g2_2p18", 3)])
+def test_fullsize_g2_golden_by_linearity(oracle, name, curve):
+    """The G2 entries of fullsize.json, re-derived another way: MSM(first half) + MSM(second half) with a
+    different thread split, compared after into_affine()."""
+    import json
+
+    g = json.load(open(os.path.join(HERE, "golden", "fullsize.json")))[name]
+    n, fq = g["n"], oracle.FQ_BYTES[curve]
+    pts, sc = oracle.gen_points(curve, 0x0BADC0DE, n), oracle.gen_scalars(curve, 0x0BADC0DE, n)
+    a = oracle.multiexp_cpu(curve, pts[: n // 2], sc[: n // 2], nthreads=3)
+    b = oracle.multiexp_cpu(curve, pts[n // 2:], sc[n // 2:], nthreads=5)
+    xy, inf = oracle.to_affine(curve, oracle.ec_op(curve, 0, a, b))
+    assert {"x": bytes(xy[0, :fq][::-1]).hex(), "y": bytes(xy[0, fq:][::-1]).hex(), "inf": int(inf[0])} == g["result"]
+
+
+def test_fullsize_bls_batched_golden_chunk(oracle):
+    """Task 5 of the 256 x 4096 BLS12-381 golden is the MSM of points / scalars [5 * 4096, 6 * 4096)."""
+    import json
+
+    g = json.load(open(os.path.join(HERE, "golden", "fullsize.json")))["bls12_381_batched_256x4096"]
+    lo, hi = 5 * 4096, 6 * 4096
+    pts, sc = oracle.gen_points(1, 0x0BADC0DE, 4096, start=lo), oracle.gen_scalars(1, 0x0BADC0DE, 4096, start=lo)
+    xy, inf = oracle.to_affine(1, oracle.multiexp_cpu(1, pts, sc))
+    assert {"x": bytes(xy[0, :48][::-1]).hex(), "y": bytes(xy[0, 48:][::-1]).hex(), "inf": int(inf[0])} == g["first_results"][5]
