@@ -86,6 +86,8 @@ void ctx_teardown(msm_ctx* ctx) {
     if (dc.copy_stream) cudaStreamDestroy(dc.copy_stream);
     for (auto& e : dc.ev_copy)
       if (e) cudaEventDestroy(e);
+    for (auto& e : dc.ev_h2d)
+      if (e) cudaEventDestroy(e);
     for (auto& e : dc.ev)
       if (e) cudaEventDestroy(e);
     if (dc.stream && dc.owns_stream) cudaStreamDestroy(dc.stream);
@@ -206,6 +208,7 @@ int msm_ctx_create(int curve, const int* device_ids, int n_devices, msm_ctx** ou
     if (e == cudaSuccess) e = cudaMalloc(&dc.small, 65536);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 8 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&dc.ev_copy[k], cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreate(&dc.ev_h2d[k]);
     if (e != cudaSuccess) {
       // a device whose kernel cannot be initialised is skipped (ec-gpu-proxy/src/multiexp.rs:288-303)
       set_error(nullptr, std::string("device init failed: ") + cudaGetErrorString(e));

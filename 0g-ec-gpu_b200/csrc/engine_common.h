@@ -62,6 +62,11 @@ struct DeviceCtx {
   void* small = nullptr;  // 64 KiB persistent (partial-point gather)
   cudaStream_t copy_stream = nullptr;  // host->device scalar chunks of pipelined calls
   cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // Host -> device rate of the last scalar upload on this device (GB/s; 0 = none yet), from ev_h2d[0..1] around the
+  // copies.  With the best device time of the shape (msm_bases::shape_best_ms) it sets how fast the sub-batches of
+  // the next pipelined call may grow (multiple_multiexp_impl).
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+  float h2d_gbs = 0.f;
 };
 
 struct FieldOps;
@@ -103,6 +108,9 @@ struct msm_bases {
   bool table_failed = false;     // the lazy build for the current shape did not fit: stop trying
   size_t shape_L = 0, table_L = 0;
   uint32_t shape_chunks = 0, shape_calls = 0, table_chunks = 0;
+  // shortest first-kernel-to-result time seen for the current shape (ms; 0 = none), and whether that was on the table
+  float shape_best_ms = 0.f;
+  bool shape_best_table = false;
 };
 
 namespace msm {

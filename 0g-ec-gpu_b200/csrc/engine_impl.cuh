@@ -82,7 +82,7 @@ template <class F> constexpr bool ba_supported() { return F::N % 4 == 0 && F::N 
 // table_c != 0: the bases are a window table built for window size table_c covering exactly L points
 template <class F>
 int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, Plan& pl, uint32_t table_c = 0,
-              uint32_t n_sub = 1, uint32_t table_stride = 0) {
+              uint32_t n_sub = 1, uint32_t table_stride = 0, double sub_ratio = 2.0) {
   if (L == 0 || num_chunks == 0 || n_lines == 0 || num_chunks > L) return MSM_ERR_INVALID;
   if (n_lines > 65535) {  // the line index is gridDim.y of the bucket kernels
     set_error(ctx, "multiple_multiexp: more than 65535 base lines per call");
@@ -103,9 +103,9 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     // Sub-batch boundaries.  Host scalars arrive back to back on the copy stream; sub-batch k can start when its
     // last byte has landed and sub-batch k-1 is done.  With sizes growing by a factor q the first (small) upload
     // is all that is exposed as long as q stays below the upload : compute speed ratio (~3.4 on one B200 with
-    // its own PCIe link; q = 2 leaves room for several GPUs pulling from one host).  MSM_B200_PIPELINE_RATIO=1
-    // gives equal sizes.
-    double q = 2.0;
+    // its own PCIe link, 1.8 with eight GPUs pulling from one host: tools/numa_h2d_probe.py).  q = 2 until the
+    // caller has measured both speeds (multiple_multiexp_impl).  MSM_B200_PIPELINE_RATIO=1 gives equal sizes.
+    double q = sub_ratio;
     if (const char* env = getenv("MSM_B200_PIPELINE_RATIO")) q = atof(env);
     if (q < 1.0) q = 1.0;
     double total = 0, w = 1;
@@ -141,10 +141,37 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   pl.n_tasks = n_lines * num_chunks;
   pl.E_max = (uint64_t)g.L * g.W;
   if (pl.E_max >= (1ull << 31) || (uint64_t)L * n_lines >= (1ull << 31)) return MSM_ERR_TOO_LARGE;
-  // slice length: enough slices to fill the machine several times over, few cut buckets
+  // Slice length: enough slices to fill the machine several times over, few cut buckets -- and a grid that is a
+  // whole number of waves, rounded DOWN.  Every slice is the same amount of work, so the blocks of k_accumulate
+  // finish wave by wave: 2^24 points at S = 332 made 4738 blocks = 8 waves of 592 and two blocks that ran a ninth
+  // wave on an empty machine (29.41 ms); S = 333, 4724 blocks, is 28.71 ms (job r2_run24; S = 380 and 443, just
+  // under 7 and 6 waves, measure the same, S = 300, 8.9 waves, 29.0).
   const uint64_t E_sub = (uint64_t)pl.sub_max * g.W;  // digits of the longest sub-batch
-  uint32_t S = (uint32_t)(E_sub / (148ull * 512 * 8));
-  if (const char* env = getenv("MSM_B200_SLICE")) S = (uint32_t)atoi(env);
+  static const uint64_t wave_slices = [] {
+    int bps = 0, sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_accumulate<F>, 128, 0) != cudaSuccess || bps < 1) bps = 4;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    cudaGetLastError();
+    return (uint64_t)sms * bps * 128;  // slices (threads) of one wave
+  }();
+  uint64_t waves = (148ull * 512 * 8 + wave_slices / 2) / wave_slices;
+  if (waves < 1) waves = 1;
+  {
+    // short rows: fewer, longer slices while that keeps them at >= 72 digits, down to 5/8 of the waves -- fewer cut
+    // buckets to fix up (2^21 points, c = 20: S = 45 in 8 waves 4.08 ms of accumulation, S = 72 in 5 waves 3.99)
+    const uint64_t w72 = E_sub / (wave_slices * 72);
+    const uint64_t w_min = (waves * 5 + 7) / 8;
+    if (w72 < waves) waves = w72 < w_min ? w_min : w72;
+  }
+  uint32_t S = (uint32_t)((E_sub + wave_slices * waves - 1) / (wave_slices * waves));
+  pl.wave_slices = (uint32_t)wave_slices;
+  pl.waves = (uint32_t)waves;
+  if (const char* env = getenv("MSM_B200_SLICE")) {
+    S = (uint32_t)atoi(env);
+    pl.waves = 0;
+  }
+  if (S < 8 || S > 1024) pl.waves = 0;
   S = S < 8 ? 8 : (S > 1024 ? 1024 : S);
   {
     // Few digits over few buckets (BLS12-381 shards of 2^19 points at c = 16: 256 digits per bucket, S = 13):
@@ -153,7 +180,10 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     // an eighth of the average bucket keep a bucket's partial slots within what one thread adds up serially.
     const uint64_t avg_bucket = E_sub / (g.NB ? g.NB : 1);
     const uint32_t s_min = (uint32_t)(avg_bucket / 8 < 64 ? avg_bucket / 8 : 64);
-    if (S < s_min && !getenv("MSM_B200_SLICE")) S = s_min;
+    if (S < s_min && !getenv("MSM_B200_SLICE")) {
+      S = s_min;
+      pl.waves = 0;
+    }
   }
   pl.S = S;
   pl.n_slices = (uint32_t)((pl.E_max + S - 1) / S);
@@ -299,8 +329,21 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
       sg.chunk_len = sg.L ? sg.L : 1;
       sg.point_offset = g.fold ? first : 0;
       E_max = (uint64_t)sg.L * g.W;
+      if (pl.waves && sg.L < pl.sub_max) {
+        // a shorter sub-batch gets its own whole number of waves (rounded down, at least one): with the longest
+        // one's slice length, 3/13 of the row next to 9/13 is 2.67 waves -- a third of a wave on an empty machine
+        uint64_t w = (uint64_t)pl.waves * sg.L / pl.sub_max;
+        if (w < 1) w = 1;
+        const uint64_t cap = (uint64_t)pl.wave_slices * w;
+        const uint64_t s_own = (E_max + cap - 1) / cap;
+        S = (uint32_t)(s_own < 8 ? 8 : (s_own > 1024 ? 1024 : s_own));
+      }
       n_slices = (uint32_t)((E_max + S - 1) / S);
       if (n_slices == 0) n_slices = 1;
+      if (n_slices > pl.slices_cap) {  // cannot happen (w <= waves); the plan's slice length always fits
+        S = pl.S;
+        n_slices = (uint32_t)((E_max + S - 1) / S);
+      }
     }
     uint32_t* counts = dc.arena.take<uint32_t>(g.NB + 1);
     uint32_t* bucket_start = dc.arena.take<uint32_t>(g.NB + 1);
@@ -466,6 +509,7 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
       mb->shape_chunks = num_chunks;
       mb->shape_calls = 1;
       mb->table_failed = false;
+      mb->shape_best_ms = 0.f;
     }
     msm_bases::Shard& shm = mb->shards[0];
     const bool fits_shape = shm.table && mb->table_L == L && mb->table_chunks == num_chunks;
@@ -521,7 +565,23 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   // measured with equal sizes (tools/e2e_timing.py, one B200): 2^20 .. 2^22 scalars are fastest in 2 sub-batches
   // (6.26 ms against 6.44 unpipelined and 6.62 in 4 at 2^21), 2^24 in 8; with sizes growing by a factor of two
   // (make_plan) four sub-batches expose the same first upload as fifteen equal ones
-  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 20)) n_sub = L >= (1u << 23) ? 4 : 2;
+  double sub_ratio = 2.0;
+  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 20)) {
+    n_sub = L >= (1u << 23) ? 4 : 2;
+    // From the second call of a shape on, both speeds are known: the upload rate of the last call on this device
+    // and the shortest device time of the shape.  Every extra sub-batch costs ~2.3 % of the call (its buckets are
+    // merged into the running ones, more slices are cut), so when the link is fast enough for sub-batches growing
+    // 3-fold, three of them (1/13, 3/13, 9/13) beat four growing 2-fold (1/15 ... 8/15): 2^24 scalars on one B200
+    // 35.55 against 36.74 ms, 2^23 19.20 against 19.66 (job r2_run23).  A slower link keeps the growth below what
+    // it can feed.
+    const msm_bases* mb = bases;
+    if (dc.h2d_gbs > 0.f && mb->shape_best_ms > 0.f && mb->shape_best_table == use_table && !getenv("MSM_B200_PIPELINE_STATIC")) {
+      const double copy_ms = (double)L * 32.0 / ((double)dc.h2d_gbs * 1e6);
+      const double r = 0.85 * (double)mb->shape_best_ms / copy_ms;
+      sub_ratio = r < 1.5 ? 1.5 : (r > 3.0 ? 3.0 : r);
+      if (L >= (1u << 23)) n_sub = sub_ratio >= 2.5 ? 3 : 4;
+    }
+  }
   if (const char* env = getenv("MSM_B200_PIPELINE")) {
     const int v = atoi(env);
     // MSM_B200_PIPELINE_DEVICE: also split device-resident rows (measurement of the split's own cost)
@@ -530,7 +590,7 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   }
   Plan pl;
   int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0, n_sub,
-                        use_table ? (uint32_t)sh0.n : 0);
+                        use_table ? (uint32_t)sh0.n : 0, sub_ratio);
   if (rc) return rc;
   if (aborted(ctx)) return MSM_ERR_ABORTED;
   const uint32_t* d_scalars;
@@ -559,6 +619,7 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
       CU_TRY(ctx, cudaStreamWaitEvent(dc.copy_stream, dc.ev[0], 0));
       drain.a = dc.copy_stream;
       drain.b = dc.stream;
+      CU_TRY(ctx, cudaEventRecord(dc.ev_h2d[0], dc.copy_stream));
       for (uint32_t sb = 0; sb < pl.n_sub; sb++) {
         const size_t first = pl.sub_first[sb], cnt = pl.sub_first[sb + 1] - first;
         if (cnt)
@@ -566,6 +627,7 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
                                       cudaMemcpyHostToDevice, dc.copy_stream));
         CU_TRY(ctx, cudaEventRecord(dc.ev_copy[sb], dc.copy_stream));
       }
+      CU_TRY(ctx, cudaEventRecord(dc.ev_h2d[1], dc.copy_stream));
     } else {
       CU_TRY(ctx, cudaMemcpyAsync(ds, scalars, L * 32, cudaMemcpyHostToDevice, dc.stream));
     }
@@ -581,6 +643,21 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
   drain.a = drain.b = nullptr;  // every sub-batch copy was waited for by the kernels that just finished
   collect_timings(ctx, dc, pl, !device_io);
+  {
+    // what the next call of this shape plans its sub-batches with
+    msm_bases* mb = const_cast<msm_bases*>(bases);
+    const float total = ctx->tm.total_ms;
+    if (total > 0.f && (mb->shape_best_ms <= 0.f || mb->shape_best_table != use_table || total < mb->shape_best_ms)) {
+      mb->shape_best_ms = total;
+      mb->shape_best_table = use_table;
+    }
+    if (!device_io && L >= (1u << 20)) {
+      float ms = 0.f;
+      if (pl.n_sub > 1) cudaEventElapsedTime(&ms, dc.ev_h2d[0], dc.ev_h2d[1]);
+      else ms = ctx->tm.h2d_ms;
+      if (ms > 0.f) dc.h2d_gbs = (float)((double)L * 32.0 / ((double)ms * 1e6));
+    }
+  }
   return MSM_OK;
 }
 

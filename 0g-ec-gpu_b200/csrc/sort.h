@@ -32,6 +32,9 @@ struct Plan {
   Geometry geo;
   uint32_t n_lines, S, n_slices, Q, RW, PG, n_tasks;
   uint32_t slices_cap;  // upper bound of the slices of one sub-batch
+  // k_accumulate grids are whole waves rounded down (make_plan): slices of one wave, waves of the longest sub-batch;
+  // waves == 0: S was imposed (environment, minimum for few buckets) and every sub-batch keeps it
+  uint32_t wave_slices = 0, waves = 0;
   uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
   uint32_t n_sub;   // sub-batches of a pipelined single-task call (they continue one shared bucket array)
   uint32_t sub_first[9];  // sub-batch k covers scalars [sub_first[k], sub_first[k+1]); sizes grow geometrically

@@ -108,6 +108,38 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons, "window": window}
 
 
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the sysfs cpulist format)."""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_cpus(device_index):
+    """The NUMA node of a GPU and the CPUs next to it, from sysfs (None when the box does not say).  A pinned host
+    buffer allocated by a thread running on those CPUs lands on the memory of the socket the GPU's PCIe link hangs
+    off, so N ranks uploading at once do not all pull through one socket's memory and the inter-socket link."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(device_index)
+        addr = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + addr
+        with open(base + "/numa_node") as f:
+            node = int(f.read().strip())
+        with open(base + "/local_cpulist") as f:
+            cpus = parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in cpus if c in allowed)
+        return {"pci": addr, "node": node, "cpus": cpus}
+    except Exception:  # noqa: BLE001 -- sysfs not exposed, attribute missing: no binding, nothing else changes
+        return None
+
+
 def sampler_extra_steps(ms_total, steps):
     """Untimed steps to append after a timed region of ms_total milliseconds (max over ranks) so that the
     clock sampler sees at least ~0.3 s of the same load.  A pure function of values that are identical on
@@ -432,6 +464,7 @@ def main():
     launches = t_last["kernel_launches"] - launches0
     result_dev = d_final.cpu().numpy().copy() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
+    e2e_sub_batches = int(ws.timings()["sub_batches"])
     result_e2e = h_out.numpy().copy() if rank == 0 else None
     ms_plain, _ = timed(step_plain, args.steps, 2)
     result_plain = d_final.cpu().numpy().copy() if rank == 0 else None
@@ -505,6 +538,7 @@ def main():
                              % (n_local * 2 * fq >> 20, n_local * 32 >> 20)},
             "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": n_total * 32, "d2h_bytes_per_step": world * chunks_local * 3 * fq,
+                    "upload_sub_batches": e2e_sub_batches,
                     "call": "msm_multiple_multiexp: host scalars (pinned) in, host point out; bases resident as in "
                             "ag_cuda_ec::multiple_multiexp"},
             "gpu_launches": int(launches + (args.steps if world > 1 else 0)),

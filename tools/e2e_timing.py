@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """End-to-end (host scalars in, host point out) timing of msm_multiple_multiexp for several
-upload pipeline depths (development aid; bench.py is the contract)."""
+upload pipeline depths (development aid; bench.py is the contract).  Depth 0 = the engine's own choice (which adapts
+to the upload rate and device time it measured on the earlier calls of the loop)."""
 import ctypes
 import json
 import os
@@ -59,6 +60,7 @@ def main():
         t = ws.timings()
         print(json.dumps({"log_n": lg, "pipeline": depth, "e2e_ms": round(best, 3), "points_per_s": round(L / best * 1e3),
                           "device_total_ms": round(t["total_ms"], 3), "h2d_ms": round(t["h2d_ms"], 3),
+                          "sub_batches": t["sub_batches"],
                           "same_result": aff == ref}))
 
 
