@@ -27,6 +27,11 @@ namespace msm {
 // groups the per-thread fix-up, the shared-memory tree and low occupancy triple that
 // (round 2, job r2_run13: 1024 .. 20480 groups reduce a bucket in 0.56 - 0.73 ns = 37 - 49 products' worth of time)
 inline double reduce_cost_per_bucket(double n_groups) { return n_groups >= 32768.0 ? 34.0 : (n_groups >= 512.0 ? 40.0 : 90.0); }
+// (A latency floor for the whole reduction -- "below ~2.4e7 bucket-products a smaller window buys nothing" -- was tried
+// and is wrong: the reduction keeps growing with the bucket count in that range too.  BN254 2^20 on tables of
+// c = 17 / 18 / 19 / 20: reduce 0.35 / 0.41 / 0.51 / 0.64 ms, call 2.96 / 3.15 / 3.07 / 2.93 ms; BLS12-381 2^19 on
+// c = 16 ... 20: reduce 0.78 / 0.81 / 1.01 / 1.36 / 1.58 ms, call 4.00 / 4.28 / 4.41 / 4.48 / 4.40 ms
+// (profiles/r02_window_sweep.log): the windows this model picks, 17 and 16, are within 1 % of the best.)
 
 inline uint32_t choose_window(uint32_t chunk_len, uint32_t bits, uint64_t n_tasks_lines, size_t xyzz_bytes,
                               double* cost_out = nullptr) {
@@ -93,8 +98,9 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   g.table_stride = table_stride ? table_stride : L;
   g.point_offset = 0;
   g.mont = ctx->scalars_mont ? (curve_is_bn254(ctx->curve) ? 1u : 2u) : 0u;
-  if (n_lines != 1 || num_chunks != 1 || n_sub < 1) n_sub = 1;
+  if (n_lines != 1 || n_sub < 1 || (num_chunks > 1 && num_chunks < 2 * n_sub)) n_sub = 1;
   pl.n_sub = n_sub;
+  pl.by_task = num_chunks > 1 && n_sub > 1;  // sub-batches are groups of whole tasks with bucket ranges of their own
   g.num_chunks = num_chunks;
   g.chunk_len = L / num_chunks;  // tail dropped, as ag-build/cl/multiexp.cl:235
   g.L = g.chunk_len * num_chunks;
@@ -114,13 +120,20 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
     w = 1;
     pl.sub_first[0] = 0;
     pl.sub_max = 0;
+    // boundaries in scalars, or in whole tasks (at least one per group) when the sub-batches are task groups
+    const uint32_t units = pl.by_task ? num_chunks : g.L, unit_len = pl.by_task ? g.chunk_len : 1;
     for (uint32_t k = 0; k < n_sub; k++, w *= q) {
       acc += w;
-      uint32_t end = k + 1 == n_sub ? g.L : (uint32_t)((double)g.L * (acc / total));
-      if (end < pl.sub_first[k]) end = pl.sub_first[k];
-      if (end > g.L) end = g.L;
-      pl.sub_first[k + 1] = end;
-      pl.sub_max = std::max(pl.sub_max, end - pl.sub_first[k]);
+      uint32_t end = k + 1 == n_sub ? units : (uint32_t)((double)units * (acc / total));
+      const uint32_t prev = pl.sub_first[k] / unit_len;
+      if (end < prev) end = prev;
+      if (pl.by_task) {
+        if (end <= prev) end = prev + 1;
+        if (end > units - (n_sub - 1 - k)) end = units - (n_sub - 1 - k);
+      }
+      if (end > units) end = units;
+      pl.sub_first[k + 1] = end * unit_len;
+      pl.sub_max = std::max(pl.sub_max, pl.sub_first[k + 1] - pl.sub_first[k]);
     }
     for (uint32_t k = n_sub + 1; k < 9; k++) pl.sub_first[k] = g.L;
   }
@@ -304,8 +317,10 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
 // the per-bucket work of the reduction is done once.
 template <class F>
 int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<F>* d_bases,
-                uint32_t line_stride, const uint32_t* d_scalars, ApiJacobian<F>* d_out, bool timed,
+                uint32_t line_stride, const uint32_t* d_scalars, ApiJacobian<F>* d_out, int timed,
                 cudaEvent_t* sub_ready = nullptr) {
+  // timed: 0 no events; 1 all phase events; 2 only the closing ones (a later task group of one call: the call's
+  // start and first-sort events stay where the first group recorded them)
   const Geometry& g = pl.geo;
   CU_TRY(ctx, dc.arena.ensure(pl.scratch_bytes));
   const uint32_t n_tiles = (g.NB + SCAN_TILE - 1) / SCAN_TILE;
@@ -316,7 +331,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
   Xyzz<F>* group_partials = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
   Xyzz<F>* group_partials2 = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
 
-  if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
+  if (timed == 1) CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
   const size_t arena_mark = dc.arena.off;
   for (uint32_t sb = 0; sb < n_sub; sb++) {
     dc.arena.off = arena_mark;  // sub-batches are stream-ordered: they reuse the same scratch
@@ -324,9 +339,16 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     uint32_t S = pl.S, n_slices = pl.n_slices;
     uint64_t E_max = pl.E_max;
     const uint32_t first = pl.sub_first[sb];
+    uint32_t bucket0 = 0;  // first bucket of this sub-batch in the call's bucket array (task groups)
     if (n_sub > 1) {
       sg.L = pl.sub_first[sb + 1] - first;
-      sg.chunk_len = sg.L ? sg.L : 1;
+      if (pl.by_task) {
+        sg.num_chunks = sg.L / g.chunk_len;
+        sg.NB = sg.num_chunks * pl.W_sets * g.B;
+        bucket0 = (first / g.chunk_len) * pl.W_sets * g.B;
+      } else {
+        sg.chunk_len = sg.L ? sg.L : 1;
+      }
       sg.point_offset = g.fold ? first : 0;
       E_max = (uint64_t)sg.L * g.W;
       if (pl.waves && sg.L < pl.sub_max) {
@@ -362,8 +384,9 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     fl.heavy_chunk0 = dc.arena.take<uint32_t>((size_t)pl.n_lines * fl.heavy_cap);
     fl.chunk_list = dc.arena.take<uint32_t>((size_t)pl.n_lines * fl.chunk_cap);
     Xyzz<F>* chunk_out = dc.arena.take<Xyzz<F>>((size_t)pl.n_lines * fl.chunk_cap);
-    Xyzz<F>* acc_sb = bucket_acc;  // every sub-batch continues the same buckets (carry_in)
-    const uint32_t carry_in = sb > 0 ? 1u : 0u;
+    // sub-batches of one MSM continue the same buckets (carry_in); task groups own disjoint bucket ranges
+    Xyzz<F>* acc_sb = bucket_acc + bucket0;
+    const uint32_t carry_in = (sb > 0 && !pl.by_task) ? 1u : 0u;
     const uint32_t* sc_sb = d_scalars + (size_t)first * 8;
     const PackedAffine<F>* bases_sb = (n_sub > 1 && !g.fold) ? d_bases + first : d_bases;
 
@@ -374,12 +397,12 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
               : pl.partition   ? enqueue_sort_partition(ctx, dc, pl, sg, E_max, sc_sb, sbuf)
                                : enqueue_sort_atomic(ctx, dc, pl, sg, E_max, sc_sb, sbuf);
     if (src != MSM_OK) return src;
-    if (timed && sb == 0) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
+    if (timed == 1 && sb == 0) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
     if (aborted(ctx)) return MSM_ERR_ABORTED;
     // --- accumulate
     dim3 grid((n_slices + tb - 1) / tb, pl.n_lines);
     CU_TRY(ctx, cudaMemsetAsync(fl.counts, 0, (size_t)3 * pl.n_lines * 4, st));
-    if (!carry_in) CU_TRY(ctx, cudaMemsetAsync(acc_sb, 0, (size_t)g.NB * pl.n_lines * sizeof(Xyzz<F>), st));  // all infinity
+    if (!carry_in) CU_TRY(ctx, cudaMemsetAsync(acc_sb, 0, (size_t)sg.NB * pl.n_lines * sizeof(Xyzz<F>), st));  // all infinity
     const uint32_t* acc_starts = bucket_start;  // bucket offsets of what the XYZZ kernel walks
     bool ba_done = false;
     if constexpr (ba_supported<F>()) {
@@ -387,7 +410,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
         // affine halving rounds (bucket_affine.cuh): entries -> planes[0] -> planes[1] -> planes[0] ...
         constexpr size_t NW = F::N;
         uint32_t* planes[2] = {dc.arena.take<uint32_t>(2 * pl.ba_cap[0] * NW), dc.arena.take<uint32_t>(2 * pl.ba_cap[1] * NW)};
-        uint32_t* offs[2] = {dc.arena.take<uint32_t>(g.NB + 1), dc.arena.take<uint32_t>(g.NB + 1)};
+        uint32_t* offs[2] = {dc.arena.take<uint32_t>(sg.NB + 1), dc.arena.take<uint32_t>(sg.NB + 1)};
         uint32_t* sc_prefix = dc.arena.take<uint32_t>((size_t)pl.ba_threads * pl.ba_batch * F::N);
         uint32_t* sc_idx = dc.arena.take<uint32_t>((size_t)pl.ba_threads * pl.ba_batch);
         const uint32_t* off_in = bucket_start;
@@ -396,17 +419,17 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
         for (uint32_t r = 0; r < pl.ba_rounds; r++) {
           uint32_t* off_out = offs[r & 1];
           const SortBuffers hb{counts, off_out, cursor, tile_sums, nullptr};
-          enqueue_halve_scan(st, g, off_in, hb);
+          enqueue_halve_scan(st, sg, off_in, hb);
           BaPoints<F> pout{nullptr, nullptr, planes[r & 1], planes[r & 1] + pl.ba_cap[r & 1] * NW};
           constexpr int BPS_LO = F::N <= 8 ? 3 : 2, BPS_HI = BPS_LO + 1;
           if (r == 0 && pl.ba_bps == BPS_HI)
-            k_affine_round<F, true, BPS_HI><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, g.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
+            k_affine_round<F, true, BPS_HI><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, sg.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
           else if (r == 0)
-            k_affine_round<F, true, BPS_LO><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, g.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
+            k_affine_round<F, true, BPS_LO><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, sg.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
           else if (pl.ba_bps == BPS_HI)
-            k_affine_round<F, false, BPS_HI><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, g.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
+            k_affine_round<F, false, BPS_HI><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, sg.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
           else
-            k_affine_round<F, false, BPS_LO><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, g.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
+            k_affine_round<F, false, BPS_LO><<<ba_grid, BA_BLOCK, 0, st>>>(pin, off_in, off_out, sg.NB, pl.ba_batch, pout, sc_prefix, sc_idx);
           pin = pout;
           off_in = off_out;
           dc.launches += 5;
@@ -415,23 +438,23 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
         S = pl.S_tail;
         n_slices = pl.n_slices_tail;
         grid = dim3((n_slices + tb - 1) / tb, 1);
-        k_accumulate<F><<<grid, tb, 0, st>>>(nullptr, 0u, nullptr, acc_starts, g.NB, acc_starts + g.NB, S, n_slices, acc_sb,
+        k_accumulate<F><<<grid, tb, 0, st>>>(nullptr, 0u, nullptr, acc_starts, sg.NB, acc_starts + sg.NB, S, n_slices, acc_sb,
                                              partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap, pin.x, pin.y);
         ba_done = true;
       }
     }
     if (!ba_done)
-      k_accumulate<F><<<grid, tb, 0, st>>>(bases_sb, line_stride, entries, bucket_start, g.NB, bucket_start + g.NB,
+      k_accumulate<F><<<grid, tb, 0, st>>>(bases_sb, line_stride, entries, bucket_start, sg.NB, bucket_start + sg.NB,
                                            S, n_slices, acc_sb, partials, carry_in, fl.counts, fl.cut_list, fl.cut_cap,
                                            nullptr, nullptr);
     // at most one cut bucket per slice
-    k_fixup_cut<F><<<grid, tb, 0, st>>>(acc_starts, g.NB, S, n_slices, acc_sb, partials, fl);
+    k_fixup_cut<F><<<grid, tb, 0, st>>>(acc_starts, sg.NB, S, n_slices, acc_sb, partials, fl);
     const uint32_t hblocks = (fl.chunk_cap + 3) / 4;
     dim3 hgrid(hblocks < 148 * 8 ? hblocks : 148 * 8, pl.n_lines);
-    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(acc_starts, g.NB, S, n_slices, acc_sb, partials, fl,
+    k_fixup_heavy<F><<<hgrid, tb, tb * sizeof(Xyzz<F>), st>>>(acc_starts, sg.NB, S, n_slices, acc_sb, partials, fl,
                                                              chunk_out);
     dim3 fgrid2(hblocks < 148 ? hblocks : 148, pl.n_lines);
-    k_fixup_heavy_final<F><<<fgrid2, tb, tb * sizeof(Xyzz<F>), st>>>(acc_starts, g.NB, S, acc_sb, fl, chunk_out);
+    k_fixup_heavy_final<F><<<fgrid2, tb, tb * sizeof(Xyzz<F>), st>>>(acc_starts, sg.NB, S, acc_sb, fl, chunk_out);
     dc.launches += 9;
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[3], st));
@@ -587,6 +610,17 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
     // MSM_B200_PIPELINE_DEVICE: also split device-resident rows (measurement of the split's own cost)
     if (v >= 1 && v <= 8 && (!device_io || getenv("MSM_B200_PIPELINE_DEVICE")) && num_chunks == 1 && n_lines == 1)
       n_sub = (uint32_t)v;
+  }
+  // Many independent tasks in one row (the reference's own bench geometry, 1024 x 2^12): the row is uploaded in
+  // groups of whole tasks of doubling size; every group is sorted and accumulated into its own range of the bucket
+  // array as soon as it has landed, and ONE reduction + combine runs over all tasks at the end (a reduction per group
+  // was measured first: each is a latency-bound chain of ~50 dependent additions, 4 groups 18.8 ms = no gain over the
+  // unpipelined 18.8, job r2_run30).  1024 x 2^12 end to end: 18.77 ms in one piece, 17.62 / 17.49 / 17.69 / 18.23 /
+  // 18.78 in 2 / 3 / 4 / 6 / 8 groups (each group still costs ~0.35 ms in short sorts and partial waves).
+  if (!device_io && n_lines == 1 && num_chunks >= 16 && L >= (1u << 20)) n_sub = 3;
+  if (const char* env = getenv("MSM_B200_PIPELINE")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= 8 && !device_io && n_lines == 1 && num_chunks >= 2 * (uint32_t)v && num_chunks > 1) n_sub = (uint32_t)v;
   }
   Plan pl;
   int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0, n_sub,

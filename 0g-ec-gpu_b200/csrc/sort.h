@@ -36,7 +36,8 @@ struct Plan {
   // waves == 0: S was imposed (environment, minimum for few buckets) and every sub-batch keeps it
   uint32_t wave_slices = 0, waves = 0;
   uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
-  uint32_t n_sub;   // sub-batches of a pipelined single-task call (they continue one shared bucket array)
+  uint32_t n_sub;   // sub-batches of a pipelined call: parts of one MSM (they continue one shared bucket array) ...
+  bool by_task = false;  // ... or groups of whole tasks of a many-task row (each owns its range of the bucket array)
   uint32_t sub_first[9];  // sub-batch k covers scalars [sub_first[k], sub_first[k+1]); sizes grow geometrically
   uint32_t sub_max;       // longest sub-batch
   mutable uint32_t scatter_passes = 1;  // filled in by enqueue_msm (0: two-level partition scatter)

@@ -270,6 +270,36 @@ def test_pipelined_sub_batches(engine, oracle, ws, curve, n_sub, table_c, monkey
     assert_same_points(oracle, curve, got, oracle.multiple_multiexp(curve, pts, sc, 1), f"pipeline {n_sub}")
 
 
+@pytest.mark.parametrize("groups", [0, 3, 8])
+def test_task_groups_pipelined_upload(engine, oracle, ws, groups, monkeypatch):
+    """A row of many independent tasks (the reference's bench geometry, ag-cuda-ec/benches/multiexp.rs:19-22) is
+    uploaded in groups of whole tasks, each sorted and accumulated into its own bucket range as it lands, with one
+    reduction over all tasks at the end (enqueue_msm, Plan::by_task): 37 tasks of
+    28 411 points (+ a dropped tail, ag-build/cl/multiexp.cl:235) in 3 (default, and forced) and 8 groups, on the plain resident
+    copy and on the window table the second call builds -- every task equal to the oracle's."""
+    curve, chunks, chunk_len = 0, 37, 28411
+    L = chunks * chunk_len + 5
+    assert L >= 1 << 20
+    if groups:
+        monkeypatch.setenv("MSM_B200_PIPELINE", str(groups))
+    w = ws[curve]
+    pts, sc = _synth(engine, w, curve, L)
+    want = oracle.multiple_multiexp(curve, pts, sc, chunks)
+    bases = engine.upload_multiexp_bases(w, pts)
+    lib = engine.load_library()
+    for call in range(3):  # plain, plain + table build, table
+        got = engine.multiple_multiexp(w, bases, sc, chunks, 8, True)
+        assert w.timings()["sub_batches"] == (groups or 3)
+        assert got.shape[0] == chunks
+        assert_same_points(oracle, curve, got, want, f"task groups {groups}, call {call}")
+    # the cost model may or may not want a table for this shape; with one forced, the groups index it by point_offset
+    bases.precompute_chunked(chunk_len)
+    assert lib.msm_bases_table_window(bases._h) != 0
+    got = engine.multiple_multiexp(w, bases, sc, chunks, 8, True)
+    assert_same_points(oracle, curve, got, want, f"task groups {groups}, explicit table")
+    bases.free()
+
+
 def test_sub_batch_growth_adapts_to_measured_speeds(engine, oracle, monkeypatch):
     """The first pipelined call of a shape splits 2^23 host scalars 4-fold with sizes doubling; once the workspace has
     measured its upload rate and the shape's device time, the split follows them (3 sub-batches growing up to 3-fold
