@@ -88,6 +88,12 @@ void ctx_teardown(msm_ctx* ctx) {
       if (e) cudaEventDestroy(e);
     for (auto& e : dc.ev_h2d)
       if (e) cudaEventDestroy(e);
+    for (auto& e : dc.ev_sorted)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : dc.ev_acc)
+      if (e) cudaEventDestroy(e);
+    if (dc.ev_fork) cudaEventDestroy(dc.ev_fork);
+    if (dc.sort_stream) cudaStreamDestroy(dc.sort_stream);
     for (auto& e : dc.ev)
       if (e) cudaEventDestroy(e);
     if (dc.stream && dc.owns_stream) cudaStreamDestroy(dc.stream);
@@ -209,6 +215,14 @@ int msm_ctx_create(int curve, const int* device_ids, int n_devices, msm_ctx** ou
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 8 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&dc.ev_copy[k], cudaEventDisableTiming);
     for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreate(&dc.ev_h2d[k]);
+    if (e == cudaSuccess) {
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lowest = highest priority
+      e = cudaStreamCreateWithPriority(&dc.sort_stream, cudaStreamNonBlocking, prio_hi);
+    }
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&dc.ev_sorted[k], cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&dc.ev_acc[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&dc.ev_fork, cudaEventDisableTiming);
     if (e != cudaSuccess) {
       // a device whose kernel cannot be initialised is skipped (ec-gpu-proxy/src/multiexp.rs:288-303)
       set_error(nullptr, std::string("device init failed: ") + cudaGetErrorString(e));

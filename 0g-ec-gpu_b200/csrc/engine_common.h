@@ -67,6 +67,12 @@ struct DeviceCtx {
   // the next pipelined call may grow (multiple_multiexp_impl).
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
   float h2d_gbs = 0.f;
+  // Sub-batch k+1 of a pipelined call is sorted on this (high-priority) stream while sub-batch k is still being
+  // accumulated on `stream`: the sort lives on the load/store and shared-memory pipes, the bucket kernel on the
+  // multiplier pipe.  ev_sorted[p] / ev_acc[p]: sort output set p is ready / no longer read; ev_fork orders the
+  // sort stream behind whatever preceded the call on `stream`.
+  cudaStream_t sort_stream = nullptr;
+  cudaEvent_t ev_sorted[2] = {nullptr, nullptr}, ev_acc[2] = {nullptr, nullptr}, ev_fork = nullptr;
 };
 
 struct FieldOps;

@@ -224,9 +224,10 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   size_t b = 0;
   // the sub-batches of a pipelined call run one after the other on the stream and share this scratch;
   // sizes are upper bounds for every sub-batch (n_sub == 1: the whole call)
-  b += Arena::padded((size_t)(g.NB + 1) * 4) * 3;                            // counts, bucket_start, cursor
-  b += Arena::padded((size_t)(n_tiles + 1) * 4);                             // tile sums + grand total
-  b += Arena::padded((E_sub + g.W) * 4);                                     // entries
+  const size_t sort_sets = n_sub > 1 ? 2 : 1;  // sub-batch k+1 is sorted while k is accumulated from the other set
+  b += sort_sets * Arena::padded((size_t)(g.NB + 1) * 4) * 3;                // counts, bucket_start, cursor
+  b += sort_sets * Arena::padded((size_t)(n_tiles + 1) * 4);                 // tile sums + grand total
+  b += sort_sets * Arena::padded((E_sub + g.W) * 4);                         // entries
   // measured slower than the bucket-range passes on B200 (2^24, c = 22: 6.8 vs 5.2 ms): off unless asked for
   pl.partition = false;
   if (const char* env = getenv("MSM_B200_PARTITION")) pl.partition = atoi(env) != 0;
@@ -331,6 +332,24 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
   Xyzz<F>* group_partials = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
   Xyzz<F>* group_partials2 = dc.arena.take<Xyzz<F>>((size_t)pl.n_tasks * pl.W_sets * pl.PG);
 
+  // Sort outputs: two sets when the sub-batches of a pipelined call overlap -- sub-batch k+1 is sorted on the sort
+  // stream while sub-batch k is accumulated from the other set (MSM_B200_SORT_OVERLAP=0: one stream, one set).
+  bool overlap = n_sub > 1 && dc.sort_stream != nullptr;
+  if (const char* env = getenv("MSM_B200_SORT_OVERLAP")) overlap = overlap && atoi(env) != 0;
+  uint32_t *counts_p[2], *bucket_start_p[2], *cursor_p[2], *tile_sums_p[2], *entries_p[2];
+  for (int p = 0; p < (n_sub > 1 ? 2 : 1); p++) {
+    counts_p[p] = dc.arena.take<uint32_t>(g.NB + 1);
+    bucket_start_p[p] = dc.arena.take<uint32_t>(g.NB + 1);
+    cursor_p[p] = dc.arena.take<uint32_t>(g.NB + 1);
+    tile_sums_p[p] = dc.arena.take<uint32_t>(n_tiles + 1);
+    entries_p[p] = dc.arena.take<uint32_t>((size_t)pl.sub_max * g.W + g.W);
+  }
+  cudaStream_t sort_st = overlap ? dc.sort_stream : st;
+  if (overlap) {
+    CU_TRY(ctx, cudaEventRecord(dc.ev_fork, st));
+    CU_TRY(ctx, cudaStreamWaitEvent(sort_st, dc.ev_fork, 0));
+  }
+
   if (timed == 1) CU_TRY(ctx, cudaEventRecord(dc.ev[1], st));
   const size_t arena_mark = dc.arena.off;
   for (uint32_t sb = 0; sb < n_sub; sb++) {
@@ -367,11 +386,9 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
         n_slices = (uint32_t)((E_max + S - 1) / S);
       }
     }
-    uint32_t* counts = dc.arena.take<uint32_t>(g.NB + 1);
-    uint32_t* bucket_start = dc.arena.take<uint32_t>(g.NB + 1);
-    uint32_t* cursor = dc.arena.take<uint32_t>(g.NB + 1);
-    uint32_t* tile_sums = dc.arena.take<uint32_t>(n_tiles + 1);
-    uint32_t* entries = dc.arena.take<uint32_t>((size_t)pl.sub_max * g.W + g.W);
+    const int par = overlap ? (int)(sb & 1) : 0;
+    uint32_t *counts = counts_p[par], *bucket_start = bucket_start_p[par], *cursor = cursor_p[par];
+    uint32_t *tile_sums = tile_sums_p[par], *entries = entries_p[par];
     Xyzz<F>* partials = dc.arena.take<Xyzz<F>>((size_t)2 * pl.slices_cap * pl.n_lines);
     FixupLists fl;
     fl.n_lines = pl.n_lines;
@@ -390,13 +407,19 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
     const uint32_t* sc_sb = d_scalars + (size_t)first * 8;
     const PackedAffine<F>* bases_sb = (n_sub > 1 && !g.fold) ? d_bases + first : d_bases;
 
-    if (sub_ready) CU_TRY(ctx, cudaStreamWaitEvent(st, sub_ready[sb], 0));
+    if (sub_ready) CU_TRY(ctx, cudaStreamWaitEvent(sort_st, sub_ready[sb], 0));
+    // the set this sort writes was last read by the bucket kernels of sub-batch sb - 2
+    if (overlap && sb >= 2) CU_TRY(ctx, cudaStreamWaitEvent(sort_st, dc.ev_acc[par], 0));
     // --- sort: bucket_start[NB+1] and the entries in bucket order
     const SortBuffers sbuf{counts, bucket_start, cursor, tile_sums, entries};
-    int src = pl.sort_mode == 2 ? enqueue_sort_binned(ctx, dc, pl, sg, E_max, sc_sb, sbuf)
-              : pl.partition   ? enqueue_sort_partition(ctx, dc, pl, sg, E_max, sc_sb, sbuf)
-                               : enqueue_sort_atomic(ctx, dc, pl, sg, E_max, sc_sb, sbuf);
+    int src = pl.sort_mode == 2 ? enqueue_sort_binned(ctx, dc, pl, sg, E_max, sc_sb, sbuf, sort_st)
+              : pl.partition   ? enqueue_sort_partition(ctx, dc, pl, sg, E_max, sc_sb, sbuf, sort_st)
+                               : enqueue_sort_atomic(ctx, dc, pl, sg, E_max, sc_sb, sbuf, sort_st);
     if (src != MSM_OK) return src;
+    if (overlap) {
+      CU_TRY(ctx, cudaEventRecord(dc.ev_sorted[par], sort_st));
+      CU_TRY(ctx, cudaStreamWaitEvent(st, dc.ev_sorted[par], 0));
+    }
     if (timed == 1 && sb == 0) CU_TRY(ctx, cudaEventRecord(dc.ev[2], st));
     if (aborted(ctx)) return MSM_ERR_ABORTED;
     // --- accumulate
@@ -455,6 +478,7 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
                                                              chunk_out);
     dim3 fgrid2(hblocks < 148 ? hblocks : 148, pl.n_lines);
     k_fixup_heavy_final<F><<<fgrid2, tb, tb * sizeof(Xyzz<F>), st>>>(acc_starts, sg.NB, S, acc_sb, fl, chunk_out);
+    if (overlap) CU_TRY(ctx, cudaEventRecord(dc.ev_acc[par], st));
     dc.launches += 9;
   }
   if (timed) CU_TRY(ctx, cudaEventRecord(dc.ev[3], st));
@@ -634,9 +658,10 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   // for pinned memory): every exit before the final synchronise -- error or abort -- drains both streams
   // first, so the caller may free / unregister the buffer as soon as the call returns.
   struct Drain {
-    cudaStream_t a = nullptr, b = nullptr;
+    cudaStream_t a = nullptr, b = nullptr, c = nullptr;
     ~Drain() {
       if (a) cudaStreamSynchronize(a);
+      if (c) cudaStreamSynchronize(c);
       if (b) cudaStreamSynchronize(b);
     }
   } drain;
@@ -653,6 +678,7 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
       CU_TRY(ctx, cudaStreamWaitEvent(dc.copy_stream, dc.ev[0], 0));
       drain.a = dc.copy_stream;
       drain.b = dc.stream;
+      drain.c = dc.sort_stream;
       CU_TRY(ctx, cudaEventRecord(dc.ev_h2d[0], dc.copy_stream));
       for (uint32_t sb = 0; sb < pl.n_sub; sb++) {
         const size_t first = pl.sub_first[sb], cnt = pl.sub_first[sb + 1] - first;
@@ -670,12 +696,13 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
   rc = enqueue_msm<F>(ctx, dc, pl, static_cast<const PackedAffine<F>*>(use_table ? sh0.table : sh0.ptr), (uint32_t)L,
                       d_scalars, d_out, true, (!device_io && pl.n_sub > 1) ? dc.ev_copy : nullptr);
   if (rc) {
+    if (dc.sort_stream) cudaStreamSynchronize(dc.sort_stream);
     cudaStreamSynchronize(dc.stream);
     return rc;
   }
   if (!device_io) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, dc.stream));
   CU_TRY(ctx, cudaStreamSynchronize(dc.stream));
-  drain.a = drain.b = nullptr;  // every sub-batch copy was waited for by the kernels that just finished
+  drain.a = drain.b = drain.c = nullptr;  // every sub-batch copy was waited for by the kernels that just finished
   collect_timings(ctx, dc, pl, !device_io);
   {
     // what the next call of this shape plans its sub-batches with
@@ -838,6 +865,7 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
       rcs[j] = rc;
       errs[j] = shadow.err;
       cudaStreamSynchronize(dc.copy_stream);
+      if (dc.sort_stream) cudaStreamSynchronize(dc.sort_stream);
       cudaStreamSynchronize(dc.stream);
       return;
     }
@@ -856,6 +884,7 @@ int multiexp_impl(msm_ctx* ctx, const void* host_bases, const msm_bases* residen
       for (auto& job : jobs) {  // nothing may still read the caller's buffers when the call returns
         cudaSetDevice(ctx->devs[job.dev_idx].dev);
         cudaStreamSynchronize(ctx->devs[job.dev_idx].copy_stream);
+        if (ctx->devs[job.dev_idx].sort_stream) cudaStreamSynchronize(ctx->devs[job.dev_idx].sort_stream);
         cudaStreamSynchronize(ctx->devs[job.dev_idx].stream);
       }
       set_error(ctx, errs[j]);

@@ -656,8 +656,8 @@ static uint32_t partition_tile(uint32_t W) {
 
 // Binned sort: every per-digit atomic in shared memory (large calls).
 int enqueue_sort_binned(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                               const uint32_t* scalars, const SortBuffers& b) {
-  cudaStream_t st = dc.stream;
+                               const uint32_t* scalars, const SortBuffers& b, cudaStream_t on) {
+  cudaStream_t st = on ? on : dc.stream;
   CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
   if (sg.L == 0) {
     enqueue_bucket_scan(st, sg, b);
@@ -694,8 +694,8 @@ int enqueue_sort_binned(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geome
 // Two-level scatter with global cursor atomics in the second level (MSM_B200_PARTITION=1: measured slower
 // than both other sorts, kept as evidence).
 int enqueue_sort_partition(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                                  const uint32_t* scalars, const SortBuffers& b) {
-  cudaStream_t st = dc.stream;
+                                  const uint32_t* scalars, const SortBuffers& b, cudaStream_t on) {
+  cudaStream_t st = on ? on : dc.stream;
   CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
   const uint32_t db = 256, dg = (sg.L + db - 1) / db;
   if (dg) launch_digits<false>(dg, db, st, scalars, sg, b.counts, nullptr, 0u, sg.NB);
@@ -727,8 +727,8 @@ int enqueue_sort_partition(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Ge
 // scatter runs in bucket-range passes: each pass writes a bounded slice of `entries` at random, which the
 // 126 MB L2 partly absorbs; every pass re-reads the scalars (sequential).
 int enqueue_sort_atomic(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                               const uint32_t* scalars, const SortBuffers& b) {
-  cudaStream_t st = dc.stream;
+                               const uint32_t* scalars, const SortBuffers& b, cudaStream_t on) {
+  cudaStream_t st = on ? on : dc.stream;
   CU_TRY(ctx, cudaMemsetAsync(b.counts, 0, (size_t)(sg.NB + 1) * 4, st));
   const uint32_t db = 256, dg = (sg.L + db - 1) / db;
   if (dg) launch_digits<false>(dg, db, st, scalars, sg, b.counts, nullptr, 0u, sg.NB);

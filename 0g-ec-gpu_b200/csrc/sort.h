@@ -63,12 +63,12 @@ void enqueue_bucket_scan(cudaStream_t st, const Geometry& g, const SortBuffers& 
 void enqueue_halve_scan(cudaStream_t st, const Geometry& g, const uint32_t* off_in, const SortBuffers& b);
 // The three sorts.  All leave bucket_start[NB+1] (exclusive scan of the bucket sizes, bucket_start[NB] = number of
 // non-zero digits) and the entries in bucket order.  sg is the geometry of the (sub-)batch, E_max its digit bound;
-// temporaries come from the scratch arena.
+// temporaries come from the scratch arena; `on`: the stream to run on (default: the context's main stream).
 int enqueue_sort_binned(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                        const uint32_t* scalars, const SortBuffers& b);
+                        const uint32_t* scalars, const SortBuffers& b, cudaStream_t on = nullptr);
 int enqueue_sort_partition(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                           const uint32_t* scalars, const SortBuffers& b);
+                           const uint32_t* scalars, const SortBuffers& b, cudaStream_t on = nullptr);
 int enqueue_sort_atomic(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const Geometry& sg, uint64_t E_max,
-                        const uint32_t* scalars, const SortBuffers& b);
+                        const uint32_t* scalars, const SortBuffers& b, cudaStream_t on = nullptr);
 
 }  // namespace msm

@@ -478,7 +478,8 @@ def main():
         achieved = macs / (acc_avg_ms * 1e-3)
         roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved / 1e12,
                     "peak": IMAD_PEAK_NOMINAL / 1e12, "unit": "TMAC/s", "frac": achieved / IMAD_PEAK_NOMINAL,
-                    "traffic": None, "avg_kernel_ms": acc_avg_ms, "algorithmic_macs_per_launch": macs,
+                    "traffic": None, "avg_kernel_ms": acc_avg_ms, "kernel_ms_steps": [round(x, 3) for x in acc_timed],
+                    "algorithmic_macs_per_launch": macs,
                     "peak_source": "148 SMs x 64 int32-multiply lanes/clk x 1.965 GHz; tools/imad_peak.cu measured "
                                    "1.852e13 MAC/s (99.5 % of it) on this pool; MEASURED_PEAKS.json has no integer figure",
                     "whole_step_frac": value / world * macs_per_point / IMAD_PEAK_NOMINAL}
