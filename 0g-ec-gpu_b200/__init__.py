@@ -23,6 +23,7 @@ from ._lib import (  # noqa: F401
     EcErrorGpuTools,
     EcErrorSimple,
     build_library,
+    describe_plan,
     fq_bytes,
     library_path,
     load_library,

@@ -70,6 +70,42 @@ class Timings(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class PlanInfo(ctypes.Structure):
+    """msm_plan_info (include/msm_b200.h)."""
+    _fields_ = [
+        ("window_bits", ctypes.c_uint32),
+        ("num_windows", ctypes.c_uint32),
+        ("buckets", ctypes.c_uint32),
+        ("sub_batches", ctypes.c_uint32),
+        ("by_task", ctypes.c_uint32),
+        ("sub_first", ctypes.c_uint32 * 9),
+        ("slice_len", ctypes.c_uint32),
+        ("slices", ctypes.c_uint32),
+        ("wave_slices", ctypes.c_uint32),
+        ("waves", ctypes.c_uint32),
+        ("sort_mode", ctypes.c_uint32),
+        ("reduce_q", ctypes.c_uint32),
+        ("digits_max", ctypes.c_uint64),
+        ("scratch_bytes", ctypes.c_uint64),
+    ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["sub_first"] = list(self.sub_first)
+        return d
+
+
+def describe_plan(curve: int, n_scalars: int, n_lines: int = 1, num_chunks: int = 1, table_window_bits: int = 0,
+                  sub_batches: int = 1, growth: float = 2.0) -> dict:
+    """msm_plan_describe: the launch plan the engine makes for a call of this shape (host arithmetic, no GPU needed)."""
+    info = PlanInfo()
+    rc = load_library().msm_plan_describe(curve, n_scalars, n_lines, num_chunks, table_window_bits, sub_batches,
+                                          float(growth), ctypes.byref(info))
+    if rc != MSM_OK:
+        raise CudaError("InvalidValue" if rc == MSM_ERR_INVALID else f"msm_plan_describe: error {rc}")
+    return info.as_dict()
+
+
 def library_path() -> str:
     return _LIB
 
@@ -114,6 +150,7 @@ def load_library() -> ctypes.CDLL:
         "msm_last_error": ([vp], ctypes.c_char_p),
         "msm_last_timings": ([vp, ctypes.POINTER(Timings)], i32),
         "msm_set_window_bits": ([vp, u32], i32),
+        "msm_plan_describe": ([i32, sz, u32, u32, u32, u32, ctypes.c_double, ctypes.POINTER(PlanInfo)], i32),
         "msm_field_impl": ([vp], ctypes.c_char_p),
         "msm_bases_upload": ([vp, vp, sz, pp], i32),
         "msm_bases_upload_sharded": ([vp, vp, sz, pp], i32),

@@ -283,6 +283,17 @@ int msm_last_timings(const msm_ctx* ctx, msm_timings* out) {
   return MSM_OK;
 }
 
+int msm_plan_describe(int curve, size_t L, uint32_t n_lines, uint32_t num_chunks, uint32_t table_window_bits,
+                      uint32_t sub_batches, double growth, msm_plan_info* out) {
+  if (!out || curve < MSM_CURVE_BN254_G1 || curve > MSM_CURVE_BLS12_381_G2 || L == 0 || L >= (1ull << 31) ||
+      sub_batches > 8 || table_window_bits > 24)
+    return MSM_ERR_INVALID;
+  msm_ctx shadow;  // no devices: make_plan only reads the curve, the window override and the scalar form
+  shadow.curve = curve;
+  shadow.ops = pick_ops(curve);
+  return shadow.ops->describe_plan(&shadow, (uint32_t)L, n_lines, num_chunks, table_window_bits, sub_batches, growth, out);
+}
+
 int msm_set_window_bits(msm_ctx* ctx, uint32_t c) {
   if (!ctx || (c != 0 && (c < 2 || c > 24))) return MSM_ERR_INVALID;
   ctx->window_override = c;

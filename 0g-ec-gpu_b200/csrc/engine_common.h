@@ -160,6 +160,9 @@ struct FieldOps {
   int (*to_affine)(msm_ctx*, const void* jac, size_t count, int mont_out, void* out_xy, uint8_t* out_inf);
   int (*sum_points)(msm_ctx*, const void* d_in, size_t count, void* d_out);
   int (*ec_fft)(msm_ctx*, void* jac, uint32_t log_n, const void* omegas_mont, uint32_t n_omegas, bool device_io);
+  // make_plan without a call behind it (msm_plan_describe): host arithmetic only
+  int (*describe_plan)(msm_ctx*, uint32_t L, uint32_t n_lines, uint32_t num_chunks, uint32_t table_c, uint32_t n_sub,
+                       double growth, msm_plan_info* out);
 };
 const FieldOps* field_ops_bn254_u29();
 const FieldOps* field_ops_bn254_sat();

@@ -1183,6 +1183,30 @@ int ec_fft_impl(msm_ctx* ctx, void* jac, uint32_t log_n, const void* omegas_mont
 
 // The entry points of one field class in two halves, so that the slow-to-compile Fq2 instantiations can be split
 // over two translation units (inst_*_g2.cu: the MSM path; inst_*_g2_aux.cu: EC-FFT, helpers, test kernels).
+template <class F>
+int describe_plan_impl(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, uint32_t table_c, uint32_t n_sub,
+                       double growth, msm_plan_info* out) {
+  Plan pl;
+  const int rc = make_plan<F>(ctx, L, n_lines, num_chunks, pl, table_c, n_sub ? n_sub : 1, 0, growth > 0 ? growth : 2.0);
+  if (rc) return rc;
+  memset(out, 0, sizeof(*out));
+  out->window_bits = pl.geo.c;
+  out->num_windows = pl.geo.W;
+  out->buckets = pl.geo.NB;
+  out->sub_batches = pl.n_sub;
+  out->by_task = pl.by_task ? 1u : 0u;
+  for (int k = 0; k < 9; k++) out->sub_first[k] = pl.sub_first[k];
+  out->slice_len = pl.S;
+  out->slices = pl.n_slices;
+  out->wave_slices = pl.wave_slices;
+  out->waves = pl.waves;
+  out->sort_mode = pl.sort_mode;
+  out->reduce_q = pl.Q;
+  out->digits_max = pl.E_max;
+  out->scratch_bytes = pl.scratch_bytes;
+  return MSM_OK;
+}
+
 template <class F> void fill_field_ops_msm(FieldOps& o, const char* name) {
   o.name = name;
   o.api_point_bytes = sizeof(ApiAffine<F>);
@@ -1191,6 +1215,7 @@ template <class F> void fill_field_ops_msm(FieldOps& o, const char* name) {
   o.multiexp = &multiexp_impl<F>;
   o.convert_bases = &convert_bases_impl<F>;
   o.build_table = [](msm_ctx* c, msm_bases::Shard& sh, uint32_t w, size_t cl) { return build_table_impl<F>(c, sh, w, cl, false); };
+  o.describe_plan = &describe_plan_impl<F>;
 }
 template <class F> void fill_field_ops_aux(FieldOps& o) {
   o.synth_points = &synth_points_impl<F>;

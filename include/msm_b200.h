@@ -92,6 +92,29 @@ const char* msm_last_error(const msm_ctx* ctx);
 int msm_last_timings(const msm_ctx* ctx, msm_timings* out);
 /* Window-size override for experiments (0 = automatic).  Results never depend on it. */
 int msm_set_window_bits(msm_ctx* ctx, uint32_t c);
+/* Host-side view of the launch plan the engine makes for one multiple_multiexp call of the given shape: window size,
+ * sub-batches of the pipelined scalar upload (parts of one MSM, or groups of whole tasks of a many-task row), slice
+ * length of the bucket kernel and the waves it fills.  Pure host arithmetic: no device work, callable without a GPU
+ * (the kernel's blocks per SM then default to 4 x 148 SMs).  table_window_bits != 0: the bases are a window table of
+ * that window size; sub_batches / growth: what the call would pass (1 and 2.0 for device-resident scalars).
+ * A test and diagnostics aid with no counterpart in the reference. */
+typedef struct {
+  uint32_t window_bits, num_windows;
+  uint32_t buckets;          /* of the whole call */
+  uint32_t sub_batches;      /* after the plan's own limits (one line of bases, >= 2 tasks per group) */
+  uint32_t by_task;          /* 1: the sub-batches are groups of whole tasks with bucket ranges of their own */
+  uint32_t sub_first[9];     /* scalar index where sub-batch k starts; [sub_batches] = scalars used */
+  uint32_t slice_len;        /* sorted digits per thread of the bucket kernel (longest sub-batch) */
+  uint32_t slices;           /* threads of the bucket kernel for the whole row */
+  uint32_t wave_slices;      /* threads of one wave of the bucket kernel */
+  uint32_t waves;            /* waves of the longest sub-batch; 0: the slice length was imposed */
+  uint32_t sort_mode;        /* 0 single-level sort, 2 binned sort */
+  uint32_t reduce_q;         /* buckets per reduction thread */
+  uint64_t digits_max;       /* upper bound of the digits sorted */
+  uint64_t scratch_bytes;    /* per-call device scratch */
+} msm_plan_info;
+int msm_plan_describe(int curve, size_t L, uint32_t n_lines, uint32_t num_chunks, uint32_t table_window_bits,
+                      uint32_t sub_batches, double growth, msm_plan_info* out);
 /* Name of the field implementation behind this context ("bn254/u29", "bn254/sat32", "bls12-381/sat32"). */
 const char* msm_field_impl(const msm_ctx* ctx);
 /* Run device 0's work on a caller-owned cudaStream_t (e.g. the framework's current stream), so that
