@@ -26,6 +26,7 @@ from ._lib import (  # noqa: F401
     describe_plan,
     fq_bytes,
     library_path,
+    pipeline_shape,
     load_library,
 )
 from .multiexp import (  # noqa: F401

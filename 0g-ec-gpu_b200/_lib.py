@@ -106,6 +106,15 @@ def describe_plan(curve: int, n_scalars: int, n_lines: int = 1, num_chunks: int 
     return info.as_dict()
 
 
+def pipeline_shape(n_scalars: int, n_lines: int = 1, num_chunks: int = 1, h2d_gbs: float = 0.0, device_ms: float = 0.0):
+    """msm_pipeline_shape: (sub-batches, growth factor) of the pipelined scalar upload for a call of this shape."""
+    n, g = ctypes.c_uint32(), ctypes.c_double()
+    rc = load_library().msm_pipeline_shape(n_scalars, n_lines, num_chunks, h2d_gbs, device_ms, ctypes.byref(n), ctypes.byref(g))
+    if rc != MSM_OK:
+        raise CudaError("InvalidValue")
+    return n.value, g.value
+
+
 def library_path() -> str:
     return _LIB
 
@@ -151,6 +160,7 @@ def load_library() -> ctypes.CDLL:
         "msm_last_timings": ([vp, ctypes.POINTER(Timings)], i32),
         "msm_set_window_bits": ([vp, u32], i32),
         "msm_plan_describe": ([i32, sz, u32, u32, u32, u32, ctypes.c_double, ctypes.POINTER(PlanInfo)], i32),
+        "msm_pipeline_shape": ([sz, u32, u32, ctypes.c_float, ctypes.c_float, ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_double)], i32),
         "msm_field_impl": ([vp], ctypes.c_char_p),
         "msm_bases_upload": ([vp, vp, sz, pp], i32),
         "msm_bases_upload_sharded": ([vp, vp, sz, pp], i32),

@@ -294,6 +294,13 @@ int msm_plan_describe(int curve, size_t L, uint32_t n_lines, uint32_t num_chunks
   return shadow.ops->describe_plan(&shadow, (uint32_t)L, n_lines, num_chunks, table_window_bits, sub_batches, growth, out);
 }
 
+int msm_pipeline_shape(size_t L, uint32_t n_lines, uint32_t num_chunks, float h2d_gbs, float device_ms,
+                       uint32_t* sub_batches, double* growth) {
+  if (!sub_batches || !growth || L == 0 || n_lines == 0 || num_chunks == 0) return MSM_ERR_INVALID;
+  pipeline_shape(L, num_chunks, n_lines, h2d_gbs, device_ms, sub_batches, growth);
+  return MSM_OK;
+}
+
 int msm_set_window_bits(msm_ctx* ctx, uint32_t c) {
   if (!ctx || (c != 0 && (c < 2 || c > 24))) return MSM_ERR_INVALID;
   ctx->window_override = c;

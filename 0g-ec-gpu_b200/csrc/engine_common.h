@@ -141,6 +141,40 @@ inline uint32_t scalar_bits(int curve) { return curve_is_bn254(curve) ? 254 : 25
   } while (0)
 
 // Per-field entry points (one instantiation unit each, see engine_impl.cuh).
+// How the host scalars of one call are pipelined: number of sub-batches and the factor their sizes grow by.
+//   * One MSM (num_chunks == 1, one line of bases) from 2^20 scalars: parts of the row that continue one bucket array.
+//     Nothing measured yet (first call of a shape): 2 parts, 4 from 2^23 scalars, sizes doubling -- four doubling parts
+//     expose the same first upload as fifteen equal ones.  From the second call of a shape on, both speeds are known
+//     (h2d_gbs: upload rate of the last call on this device, device_ms: shortest device time of the shape): the parts
+//     grow by 0.85 x device time / upload time, clamped to 1.5 .. 3.  Every extra part costs ~2.3 % of the call (its
+//     buckets are merged into the running ones, more slices are cut), so when the link feeds 3-fold growth, three parts
+//     (1/13, 3/13, 9/13) beat four growing 2-fold (1/15 ... 8/15): 2^24 scalars on one B200 35.55 against 36.74 ms,
+//     2^23 19.20 against 19.66 (job r2_run23); a slower link keeps the growth below what it can feed.
+//   * Many independent tasks in one row (the reference's bench geometry, 1024 x 2^12; one line, >= 16 tasks, from 2^20
+//     scalars): 3 groups of whole tasks, sizes doubling.  Every group is sorted and accumulated into its own range of
+//     the bucket array as soon as it has landed, and ONE reduction + combine runs over all tasks at the end (a
+//     reduction per group was measured first: each is a latency-bound chain of ~50 dependent additions, 4 groups
+//     18.8 ms = no gain, job r2_run30).  1024 x 2^12 end to end: 18.77 ms in one piece, 17.62 / 17.49 / 17.69 / 18.23 /
+//     18.78 in 2 / 3 / 4 / 6 / 8 groups (each group still costs ~0.35 ms in short sorts and partial waves).
+//   * Everything else (several lines of bases, short rows): one piece.
+inline void pipeline_shape(size_t L, uint32_t num_chunks, uint32_t n_lines, float h2d_gbs, float device_ms,
+                           uint32_t* n_sub, double* growth) {
+  *n_sub = 1;
+  *growth = 2.0;
+  if (n_lines != 1 || L < (1u << 20)) return;
+  if (num_chunks == 1) {
+    *n_sub = L >= (1u << 23) ? 4 : 2;
+    if (h2d_gbs > 0.f && device_ms > 0.f) {
+      const double copy_ms = (double)L * 32.0 / ((double)h2d_gbs * 1e6);
+      const double r = 0.85 * (double)device_ms / copy_ms;
+      *growth = r < 1.5 ? 1.5 : (r > 3.0 ? 3.0 : r);
+      if (L >= (1u << 23)) *n_sub = *growth >= 2.5 ? 3 : 4;
+    }
+  } else if (num_chunks >= 16) {
+    *n_sub = 3;
+  }
+}
+
 struct FieldOps {
   const char* name;
   size_t api_point_bytes;     // {x,y} at the API boundary

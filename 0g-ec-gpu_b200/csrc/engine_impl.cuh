@@ -605,46 +605,22 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
                   fold_cost(sh0.table_c, chunk_len, scalar_bits(ctx->curve), groups) < plain_cost;
     }
   }
-  // Host scalars of one large single-task call arrive in n_sub chunks on a copy stream while the
-  // previous chunk is already being sorted and accumulated (the 32 B/scalar upload is ~20 % of the
-  // call otherwise).
+  // Host scalars of a large call arrive in sub-batches on a copy stream while the previous sub-batch is already being
+  // sorted and accumulated (pipeline_shape above; the 32 B/scalar upload is ~20 % of the call otherwise).
   uint32_t n_sub = 1;
-  // measured with equal sizes (tools/e2e_timing.py, one B200): 2^20 .. 2^22 scalars are fastest in 2 sub-batches
-  // (6.26 ms against 6.44 unpipelined and 6.62 in 4 at 2^21), 2^24 in 8; with sizes growing by a factor of two
-  // (make_plan) four sub-batches expose the same first upload as fifteen equal ones
   double sub_ratio = 2.0;
-  if (!device_io && num_chunks == 1 && n_lines == 1 && L >= (1u << 20)) {
-    n_sub = L >= (1u << 23) ? 4 : 2;
-    // From the second call of a shape on, both speeds are known: the upload rate of the last call on this device
-    // and the shortest device time of the shape.  Every extra sub-batch costs ~2.3 % of the call (its buckets are
-    // merged into the running ones, more slices are cut), so when the link is fast enough for sub-batches growing
-    // 3-fold, three of them (1/13, 3/13, 9/13) beat four growing 2-fold (1/15 ... 8/15): 2^24 scalars on one B200
-    // 35.55 against 36.74 ms, 2^23 19.20 against 19.66 (job r2_run23).  A slower link keeps the growth below what
-    // it can feed.
+  if (!device_io) {
     const msm_bases* mb = bases;
-    if (dc.h2d_gbs > 0.f && mb->shape_best_ms > 0.f && mb->shape_best_table == use_table && !getenv("MSM_B200_PIPELINE_STATIC")) {
-      const double copy_ms = (double)L * 32.0 / ((double)dc.h2d_gbs * 1e6);
-      const double r = 0.85 * (double)mb->shape_best_ms / copy_ms;
-      sub_ratio = r < 1.5 ? 1.5 : (r > 3.0 ? 3.0 : r);
-      if (L >= (1u << 23)) n_sub = sub_ratio >= 2.5 ? 3 : 4;
-    }
+    const bool measured = mb->shape_best_table == use_table && !getenv("MSM_B200_PIPELINE_STATIC");
+    pipeline_shape(L, num_chunks, n_lines, measured ? dc.h2d_gbs : 0.f, measured ? mb->shape_best_ms : 0.f, &n_sub, &sub_ratio);
   }
   if (const char* env = getenv("MSM_B200_PIPELINE")) {
     const int v = atoi(env);
     // MSM_B200_PIPELINE_DEVICE: also split device-resident rows (measurement of the split's own cost)
-    if (v >= 1 && v <= 8 && (!device_io || getenv("MSM_B200_PIPELINE_DEVICE")) && num_chunks == 1 && n_lines == 1)
-      n_sub = (uint32_t)v;
-  }
-  // Many independent tasks in one row (the reference's own bench geometry, 1024 x 2^12): the row is uploaded in
-  // groups of whole tasks of doubling size; every group is sorted and accumulated into its own range of the bucket
-  // array as soon as it has landed, and ONE reduction + combine runs over all tasks at the end (a reduction per group
-  // was measured first: each is a latency-bound chain of ~50 dependent additions, 4 groups 18.8 ms = no gain over the
-  // unpipelined 18.8, job r2_run30).  1024 x 2^12 end to end: 18.77 ms in one piece, 17.62 / 17.49 / 17.69 / 18.23 /
-  // 18.78 in 2 / 3 / 4 / 6 / 8 groups (each group still costs ~0.35 ms in short sorts and partial waves).
-  if (!device_io && n_lines == 1 && num_chunks >= 16 && L >= (1u << 20)) n_sub = 3;
-  if (const char* env = getenv("MSM_B200_PIPELINE")) {
-    const int v = atoi(env);
-    if (v >= 1 && v <= 8 && !device_io && n_lines == 1 && num_chunks >= 2 * (uint32_t)v && num_chunks > 1) n_sub = (uint32_t)v;
+    if (v >= 1 && v <= 8 && n_lines == 1) {
+      if (num_chunks == 1 && (!device_io || getenv("MSM_B200_PIPELINE_DEVICE"))) n_sub = (uint32_t)v;
+      if (num_chunks > 1 && !device_io && num_chunks >= 2 * (uint32_t)v) n_sub = (uint32_t)v;
+    }
   }
   Plan pl;
   int rc = make_plan<F>(ctx, (uint32_t)L, n_lines, num_chunks, pl, use_table ? sh0.table_c : 0, n_sub,

@@ -115,6 +115,12 @@ typedef struct {
 } msm_plan_info;
 int msm_plan_describe(int curve, size_t L, uint32_t n_lines, uint32_t num_chunks, uint32_t table_window_bits,
                       uint32_t sub_batches, double growth, msm_plan_info* out);
+/* How the engine pipelines the upload of the host scalars of one multiple_multiexp call: the number of sub-batches
+ * (parts of one MSM, or groups of whole tasks of a many-task row) and the factor their sizes grow by.  h2d_gbs and
+ * device_ms are what a workspace has measured on earlier calls of the shape (upload rate in GB/s, shortest device time
+ * in ms); 0 = nothing measured yet.  Pure host arithmetic, like msm_plan_describe. */
+int msm_pipeline_shape(size_t L, uint32_t n_lines, uint32_t num_chunks, float h2d_gbs, float device_ms,
+                       uint32_t* sub_batches, double* growth);
 /* Name of the field implementation behind this context ("bn254/u29", "bn254/sat32", "bls12-381/sat32"). */
 const char* msm_field_impl(const msm_ctx* ctx);
 /* Run device 0's work on a caller-owned cudaStream_t (e.g. the framework's current stream), so that

@@ -110,3 +110,40 @@ def test_invalid_shapes(engine):
             engine.describe_plan(0, **args)
     with pytest.raises(engine.CudaError):
         engine.describe_plan(7, 100)
+
+
+def test_pipeline_shape_before_anything_is_measured(engine):
+    """First call of a shape: short rows in one piece, one MSM in 2 parts from 2^20 scalars and 4 from 2^23 (sizes
+    doubling), a many-task row in 3 task groups, several lines of bases in one piece."""
+    ps = engine.pipeline_shape
+    assert ps((1 << 20) - 1) == (1, 2.0)
+    assert ps(1 << 20) == (2, 2.0) and ps((1 << 23) - 1) == (2, 2.0)
+    assert ps(1 << 23) == (4, 2.0) and ps(1 << 24) == (4, 2.0)
+    assert ps(1 << 22, num_chunks=1024) == (3, 2.0)
+    assert ps(1 << 22, num_chunks=8) == (1, 2.0)                   # too few tasks for groups
+    assert ps(1 << 19, num_chunks=128) == (1, 2.0)                 # an eighth of the batched row on one of 8 GPUs
+    assert ps(1 << 21, n_lines=10, num_chunks=2048) == (1, 2.0)    # the AMT shape: 10 lines share the scalar row
+
+
+def test_pipeline_shape_follows_the_measured_speeds(engine):
+    """From the second call on the growth is 0.85 x device time / upload time, clamped to 1.5 .. 3; three parts when it
+    reaches 2.5 (from 2^23 scalars), four otherwise."""
+    ps = engine.pipeline_shape
+    # one B200 with the PCIe link to itself: 55 GB/s, 2^24 points in 32.7 ms -> upload 9.76 ms, ratio 3.35
+    n, g = ps(1 << 24, h2d_gbs=55.0, device_ms=32.7)
+    assert n == 3 and abs(g - 0.85 * 32.7 / (536.870912 / 55.0)) < 1e-5 and 2.8 < g < 2.9
+    # eight ranks on one host: 23 GB/s to a 2^21-point shard that takes 5.1 ms on the device -> 0.85 x 1.75 = 1.49,
+    # held at the floor of 1.5; two parts
+    assert ps(1 << 21, h2d_gbs=23.0, device_ms=5.1) == (2, 1.5)
+    n, g = ps(1 << 21, h2d_gbs=36.0, device_ms=5.1)  # the four GPUs of that box with the faster links
+    assert n == 2 and abs(g - 0.85 * 5.1 / (67.108864 / 36.0)) < 1e-5 and 2.3 < g < 2.4
+    # a slow link under a large row: growth stays at the floor, four parts
+    assert ps(1 << 24, h2d_gbs=12.0, device_ms=32.7) == (4, 1.5)
+    # a very fast link: capped at 3
+    assert ps(1 << 24, h2d_gbs=400.0, device_ms=32.7) == (3, 3.0)
+    # only one of the two speeds known: as if nothing had been measured
+    assert ps(1 << 24, h2d_gbs=55.0) == (4, 2.0) and ps(1 << 24, device_ms=32.7) == (4, 2.0)
+    # task groups do not adapt
+    assert ps(1 << 22, num_chunks=1024, h2d_gbs=55.0, device_ms=16.3) == (3, 2.0)
+    with pytest.raises(engine.CudaError):
+        ps(0)
