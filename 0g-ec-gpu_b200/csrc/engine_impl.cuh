@@ -160,22 +160,33 @@ int make_plan(msm_ctx* ctx, uint32_t L, uint32_t n_lines, uint32_t num_chunks, P
   // wave on an empty machine (29.41 ms); S = 333, 4724 blocks, is 28.71 ms (job r2_run24; S = 380 and 443, just
   // under 7 and 6 waves, measure the same, S = 300, 8.9 waves, 29.0).
   const uint64_t E_sub = (uint64_t)pl.sub_max * g.W;  // digits of the longest sub-batch
-  static const uint64_t wave_slices = [] {
-    int bps = 0, sms = 0, dev = 0;
-    cudaGetDevice(&dev);
+  static const int acc_bps = [] {
+    int bps = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_accumulate<F>, 128, 0) != cudaSuccess || bps < 1) bps = 4;
+    cudaGetLastError();
+    return bps;
+  }();
+  static const uint64_t wave_slices = [] {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
     cudaGetLastError();
-    return (uint64_t)sms * bps * 128;  // slices (threads) of one wave
+    return (uint64_t)sms * acc_bps * 128;  // slices (threads) of one wave
   }();
+  pl.acc_blocks_per_sm = (uint32_t)acc_bps;
   uint64_t waves = (148ull * 512 * 8 + wave_slices / 2) / wave_slices;
   if (waves < 1) waves = 1;
   {
-    // short rows: fewer, longer slices while that keeps them at >= 72 digits, down to 5/8 of the waves -- fewer cut
-    // buckets to fix up (2^21 points, c = 20: S = 45 in 8 waves 4.08 ms of accumulation, S = 72 in 5 waves 3.99)
-    const uint64_t w72 = E_sub / (wave_slices * 72);
+    // Fewer, longer slices -- down to 5/8 of the waves -- while that gets them to 72 digits (short rows) or to 4/3 of
+    // the average bucket: a slice shorter than a bucket cuts every bucket it touches, and every cut is a full addition
+    // in k_fixup_cut.  BN254 2^21 points, c = 20 (52 digits per bucket): S = 45 in 8 waves 4.08 ms of accumulation,
+    // S = 72 in 5 waves 3.99; BLS12-381 2^22, c = 20 (104 per bucket, k_fixup_cut 0.61 ms): S = 88 in 11 waves 21.11 ms
+    // per call, S = 138 in 7 waves 20.82 (jobs r2_run25, r2_run40).
+    const uint64_t avg_bucket = (pl.by_task ? pl.E_max : E_sub) / (NB ? NB : 1);  // a task group has its share of both
+    const uint64_t s_target = std::max<uint64_t>(72, avg_bucket * 4 / 3);
+    const uint64_t w_want = (E_sub + wave_slices * s_target / 2) / (wave_slices * s_target);  // nearest
     const uint64_t w_min = (waves * 5 + 7) / 8;
-    if (w72 < waves) waves = w72 < w_min ? w_min : w72;
+    if (w_want < waves) waves = w_want < w_min ? w_min : w_want;
   }
   uint32_t S = (uint32_t)((E_sub + wave_slices * waves - 1) / (wave_slices * waves));
   pl.wave_slices = (uint32_t)wave_slices;
@@ -334,8 +345,11 @@ int enqueue_msm(msm_ctx* ctx, DeviceCtx& dc, const Plan& pl, const PackedAffine<
 
   // Sort outputs: two sets when the sub-batches of a pipelined call overlap -- sub-batch k+1 is sorted on the sort
   // stream while sub-batch k is accumulated from the other set (MSM_B200_SORT_OVERLAP=0: one stream, one set).
-  bool overlap = n_sub > 1 && dc.sort_stream != nullptr;
-  if (const char* env = getenv("MSM_B200_SORT_OVERLAP")) overlap = overlap && atoi(env) != 0;
+  // Only where the bucket kernel keeps 4 blocks on an SM (BN254 G1): a sort block takes the place of two of them, and
+  // the two that remain still keep the multiplier pipe busy.  BLS12-381 has 3 (168 registers): one left per scheduler
+  // is not enough -- its 2^22-point row split in two takes 22.1 ms on one stream and 23.2 ms overlapped (job r2_run39).
+  bool overlap = n_sub > 1 && dc.sort_stream != nullptr && pl.acc_blocks_per_sm >= 4;
+  if (const char* env = getenv("MSM_B200_SORT_OVERLAP")) overlap = n_sub > 1 && dc.sort_stream != nullptr && atoi(env) != 0;
   uint32_t *counts_p[2], *bucket_start_p[2], *cursor_p[2], *tile_sums_p[2], *entries_p[2];
   for (int p = 0; p < (n_sub > 1 ? 2 : 1); p++) {
     counts_p[p] = dc.arena.take<uint32_t>(g.NB + 1);

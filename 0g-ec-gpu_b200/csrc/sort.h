@@ -35,6 +35,7 @@ struct Plan {
   // k_accumulate grids are whole waves rounded down (make_plan): slices of one wave, waves of the longest sub-batch;
   // waves == 0: S was imposed (environment, minimum for few buckets) and every sub-batch keeps it
   uint32_t wave_slices = 0, waves = 0;
+  uint32_t acc_blocks_per_sm = 4;  // resident blocks of the bucket kernel per SM (occupancy API; 4 without a device)
   uint32_t W_sets;  // bucket sets per task: W, or 1 when the bases are a folded window table
   uint32_t n_sub;   // sub-batches of a pipelined call: parts of one MSM (they continue one shared bucket array) ...
   bool by_task = false;  // ... or groups of whole tasks of a many-task row (each owns its range of the bucket array)
