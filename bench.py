@@ -23,7 +23,7 @@ device.  Total work is fixed => "scaling": "strong".
 Timing: CUDA events on the stream every kernel is launched on (the engine is switched onto torch's
 current stream), barrier + synchronize on both sides, max over ranks.  Inputs per step (1 GiB of
 bases, 0.5 GiB of scalars, >= 0.8 GiB of sorted digits) exceed the 126 MB L2 many times over.
-Clocks: nvidia-smi sampled every 50 ms from before the warm-up; when the timed region is shorter than
+Clocks: nvidia-smi sampled every 100 ms from before the warm-up; when the timed region is shorter than
 that, the same step keeps running for ~0.3 s after it -- the SAME number of extra steps on every rank
 (sampler_extra_steps: a function of the all-reduced time), because a step holds a collective.
 
@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -438,7 +438,7 @@ def main():
         ms = float(ms.item())
         clocks = None
         if sampler is not None:  # every rank passes one (rank-uniform branch: it holds collectives)
-            # Keep the same load up until nvidia-smi (50 ms period) has seen it.  The step holds a collective
+            # Keep the same load up until nvidia-smi (100 ms period) has seen it.  The step holds a collective
             # when world > 1, so every rank must run the SAME number of extra steps: the count comes from the
             # all-reduced time, never from a local clock.
             for _ in range(sampler_extra_steps(ms, steps)):
