@@ -72,3 +72,44 @@ def test_golden_check_accepts_the_golden_and_rejects_anything_else():
     rows = g["bn254_batched_1024x4096"]["results"]
     assert bench.golden_check(0, 22, True, affine_bytes(rows), 32) == (True, "bn254_batched_1024x4096")
     assert bench.golden_check(0, 22, True, affine_bytes(rows[::-1]), 32)[0] is False
+
+
+def test_cpulist_and_numa_lookup_degrade_quietly():
+    """bench.parse_cpulist reads sysfs' cpulist format; gpu_numa_cpus returns None where there is no GPU / no sysfs entry
+    (it only ever informs where a pinned buffer is allocated)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+
+    assert bench.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert bench.parse_cpulist("5") == [5] and bench.parse_cpulist("") == []
+    assert bench.gpu_numa_cpus(0) is None  # no GPU in this container
+
+
+def test_clock_sampler_summary_without_nvidia_smi(monkeypatch):
+    """ClockSampler: rows inside the timed window are picked; a region shorter than the sampling period falls back to
+    every sample under load; throttle reasons are reported by name; no nvidia-smi -> says so."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+    class FakeThread:
+        def join(self, timeout=None):
+            pass
+
+    def sampler(rows):
+        s = bench.ClockSampler(0)
+        s.proc, s.thread, s.rows = FakeProc(), FakeThread(), rows
+        return s
+
+    idle = ["345", "1965", "140.0", "Not Active", "Not Active", "Not Active", "Not Active"]
+    busy = ["1965", "1965", "640.5", "Not Active", "Not Active", "Not Active", "Active"]
+    rows = [[0.0] + idle, [1.0] + busy, [1.1] + busy, [1.2] + busy, [2.0] + idle]
+    c = sampler([list(r) for r in rows]).stop(0.95, 1.25)
+    assert c["window"] == "timed region" and c["samples"] == 3 and c["sm_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"]
+    c = sampler([list(r) for r in rows]).stop(1.04, 1.06)  # no sample inside: every sample, idle ones filtered by power
+    assert c["window"].startswith("warm-up") and c["samples"] == 5 and c["sm_mhz"] == 1965.0 and c["power_w_max"] == 640.5
+    s = bench.ClockSampler(0)
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
