@@ -147,3 +147,46 @@ def test_pipeline_shape_follows_the_measured_speeds(engine):
     assert ps(1 << 22, num_chunks=1024, h2d_gbs=55.0, device_ms=16.3) == (3, 2.0)
     with pytest.raises(engine.CudaError):
         ps(0)
+
+
+def test_plan_invariants_over_random_shapes(engine):
+    """Whatever the shape: sub-batches are contiguous and cover exactly the scalars used, task groups are whole tasks,
+    the slices cover every digit, and a grid sized in waves never spills into one more."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(curve=st.integers(0, 3), log_l=st.integers(4, 25), jitter=st.integers(0, 1000), chunks_log=st.integers(0, 12),
+           chunk_jitter=st.integers(0, 3), n_lines=st.sampled_from([1, 1, 1, 2, 10]), n_sub=st.integers(1, 8),
+           growth=st.sampled_from([1.0, 1.5, 2.0, 2.9, 3.0]), table=st.booleans())
+    def check(curve, log_l, jitter, chunks_log, chunk_jitter, n_lines, n_sub, growth, table):
+        L = (1 << log_l) + jitter
+        num_chunks = min((1 << chunks_log) + chunk_jitter, L)
+        table_c = 0
+        if table:
+            table_c = min(22, max(8, log_l - chunks_log))
+        try:
+            p = engine.describe_plan(curve, L, n_lines=n_lines, num_chunks=num_chunks, table_window_bits=table_c,
+                                     sub_batches=n_sub, growth=growth)
+        except engine.CudaError:
+            return  # too many buckets / digits for 32-bit indices: rejected, not planned
+        chunk_len = L // num_chunks
+        used = chunk_len * num_chunks
+        k = p["sub_batches"]
+        first = p["sub_first"]
+        assert 1 <= k <= n_sub and first[0] == 0 and first[k] == used
+        assert all(first[i] <= first[i + 1] for i in range(k))
+        if p["by_task"]:
+            assert n_lines == 1 and num_chunks >= 2 * k
+            assert all(first[i] < first[i + 1] and first[i] % chunk_len == 0 for i in range(k))
+        if n_lines != 1:
+            assert k == 1
+        assert p["digits_max"] == used * p["num_windows"]
+        assert p["slices"] * p["slice_len"] >= p["digits_max"] and 8 <= p["slice_len"] <= 1024
+        sets = 1 if table_c else p["num_windows"]
+        assert p["buckets"] == num_chunks * sets << (p["window_bits"] - 1)
+        if p["waves"]:
+            longest = max(first[i + 1] - first[i] for i in range(k))
+            assert -(-longest * p["num_windows"] // p["slice_len"]) <= p["waves"] * p["wave_slices"]
+
+    check()
