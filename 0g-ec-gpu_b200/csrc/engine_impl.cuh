@@ -704,8 +704,17 @@ int multiple_multiexp_impl(msm_ctx* ctx, const msm_bases* bases, const void* sca
     }
     if (!device_io && L >= (1u << 20)) {
       float ms = 0.f;
-      if (pl.n_sub > 1) cudaEventElapsedTime(&ms, dc.ev_h2d[0], dc.ev_h2d[1]);
-      else ms = ctx->tm.h2d_ms;
+      if (pl.n_sub > 1) {
+        // the copy stream recorded this event right after the last sub-batch's copy, which the kernels that just
+        // finished had waited for: the wait below returns at once, and the elapsed-time query cannot come back
+        // "not ready" (an error code the next cudaGetLastError would otherwise pick up)
+        if (cudaEventSynchronize(dc.ev_h2d[1]) != cudaSuccess || cudaEventElapsedTime(&ms, dc.ev_h2d[0], dc.ev_h2d[1]) != cudaSuccess) {
+          ms = 0.f;
+          cudaGetLastError();
+        }
+      } else {
+        ms = ctx->tm.h2d_ms;
+      }
       if (ms > 0.f) dc.h2d_gbs = (float)((double)L * 32.0 / ((double)ms * 1e6));
     }
   }
