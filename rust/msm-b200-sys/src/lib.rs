@@ -52,6 +52,11 @@ extern "C" {
     pub fn msm_bases_precompute_chunked(ctx: *mut msm_ctx, b: *mut msm_bases, chunk_len: usize) -> c_int;
     /// 0 = off, 1 = lazy (default: the 2nd call of a shape builds the window table), 2 = eager.
     pub fn msm_bases_set_table_policy(ctx: *mut msm_ctx, b: *mut msm_bases, policy: c_int) -> c_int;
+    /// Upload pipelining the engine would use for a call shape (host arithmetic, no device work): sub-batches of one
+    /// MSM or task groups of a many-task row, and the factor their sizes grow by.
+    pub fn msm_pipeline_shape(
+        l: usize, n_lines: u32, num_chunks: u32, h2d_gbs: f32, device_ms: f32, sub_batches: *mut u32, growth: *mut f64,
+    ) -> c_int;
     pub fn msm_bases_size_bytes(b: *const msm_bases) -> usize;
     pub fn msm_bases_free(b: *mut msm_bases) -> c_int;
     pub fn msm_multiple_multiexp(
