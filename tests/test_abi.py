@@ -124,10 +124,16 @@ def test_header_is_valid_c99_and_cpp(tmp_path):
     src.write_text('#include "msm_b200.h"\n#include <stdio.h>\n'
                    "int main(void) { msm_ctx* c = 0; int rc = msm_ctx_create(MSM_CURVE_BN254_G1, 0, 1, &c);\n"
                    '  printf("%s rc=%d devices=%d\\n", msm_version(), rc, msm_device_count());\n'
-                   "  if (rc == MSM_OK) msm_ctx_destroy(c); return 0; }\n")
+                   "  if (rc == MSM_OK) msm_ctx_destroy(c);\n"
+                   "  msm_plan_info p; unsigned n = 0; double g = 0;\n"  # the two host-only calls work from plain C, GPU or not
+                   "  if (msm_plan_describe(MSM_CURVE_BN254_G1, (size_t)1 << 24, 1, 1, 22, 1, 2.0, &p) != MSM_OK) return 2;\n"
+                   "  if (msm_pipeline_shape((size_t)1 << 24, 1, 1, 55.0f, 32.7f, &n, &g) != MSM_OK) return 3;\n"
+                   '  printf("plan c=%u W=%u S=%u sub=%u growth=%.2f\\n", p.window_bits, p.num_windows, p.slice_len, n, g);\n'
+                   "  return 0; }\n")
     exe = tmp_path / "caller"
     so_dir = os.path.join(ROOT, "0g-ec-gpu_b200")
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                            "-L", so_dir, "-lmsm_b200", "-Wl,-rpath," + so_dir])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "msm_b200" in out.stdout, out.stdout + out.stderr
+    assert "plan c=22 W=12 S=333 sub=3 growth=2.85" in out.stdout, out.stdout
